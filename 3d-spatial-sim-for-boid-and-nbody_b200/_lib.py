@@ -1,0 +1,100 @@
+"""ctypes binding of libb200sim.so (C ABI: include/b200sim.h).
+
+There is no CPU fallback: if the library is missing or fails to load, importing a symbol
+raises.  The library is built in-tree by build.py (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+N_PHASES = 8
+PHASE_NAMES = ("keygen", "sort", "gather", "build", "extract", "traverse", "exchange", "integrate")
+
+
+class NBodyStats(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64), ("steps", C.c_int64), ("records", C.c_int64), ("interactions", C.c_int64),
+        ("bounds", C.c_double), ("error_flags", C.c_uint32), ("sm_count", C.c_int32),
+        ("bytes_allocated", C.c_int64), ("timed_steps", C.c_int64), ("phase_ms", C.c_double * N_PHASES),
+    ]
+
+
+class B200Error(RuntimeError):
+    """Raised for every non-zero status of the C ABI (callers of the reference backend catch
+    Exception around construction: nbody/simulation.py:533-540, tools/record.py:781-784)."""
+
+
+_dp, _fp = C.POINTER(C.c_double), C.POINTER(C.c_float)
+_h = C.c_void_p
+
+# name -> (restype, argtypes); every entry must be declared in include/b200sim.h
+SIGNATURES = {
+    "b200_last_error": (C.c_char_p, []),
+    "b200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "b200_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_int]),
+    "b200_nbody_create": (C.c_int, [C.c_int64, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double,
+                                    C.c_int, C.POINTER(_h)]),
+    "b200_nbody_destroy": (C.c_int, [_h]),
+    "b200_nbody_step": (C.c_int, [_h, C.c_double]),
+    "b200_nbody_step_n": (C.c_int, [_h, C.c_double, C.c_int]),
+    "b200_nbody_compute_accelerations": (C.c_int, [_h, _fp]),
+    "b200_nbody_compute_colors": (C.c_int, [_h, C.c_double]),
+    "b200_nbody_get_positions": (C.c_int, [_h, _fp]),
+    "b200_nbody_get_positions_f64": (C.c_int, [_h, _dp]),
+    "b200_nbody_get_velocities": (C.c_int, [_h, _dp]),
+    "b200_nbody_get_colors": (C.c_int, [_h, _fp]),
+    "b200_nbody_sync": (C.c_int, [_h]),
+    "b200_nbody_set_state": (C.c_int, [_h, _dp, _dp]),
+    "b200_nbody_set_params": (C.c_int, [_h, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "b200_nbody_get_keys": (C.c_int, [_h, C.POINTER(C.c_uint64)]),
+    "b200_nbody_get_perm": (C.c_int, [_h, C.POINTER(C.c_uint32)]),
+    "b200_nbody_get_stats": (C.c_int, [_h, C.POINTER(NBodyStats)]),
+    "b200_nbody_reset_stats": (C.c_int, [_h]),
+    "b200_nbody_set_profiling": (C.c_int, [_h, C.c_int]),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if the sources are newer) and type every entry point."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB_PATH
+        if _build.is_stale():
+            try:
+                _build.build()
+            except Exception as e:  # no nvcc on this box and no prebuilt library
+                if not os.path.exists(path):
+                    raise B200Error(f"libb200sim.so is not built and cannot be built here: {e}") from e
+        L = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)   # AttributeError if the library lacks a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load().b200_last_error()
+        raise B200Error(f"libb200sim status {status}: {msg.decode() if msg else 'unknown error'}")
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    st = load().b200_device_count(C.byref(n))
+    return int(n.value) if st == 0 else 0
+
+
+def device_info(device: int = 0) -> str:
+    buf = C.create_string_buffer(256)
+    check(load().b200_device_info(device, buf, 256))
+    return buf.value.decode()

@@ -1,0 +1,230 @@
+// capi.cu -- extern "C" boundary of libb200sim.so (see include/b200sim.h).
+#include "../../include/b200sim.h"
+#include "nbody.cuh"
+
+#include <string.h>
+
+namespace b200 {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace b200
+
+struct b200_nbody {
+    b200::NBodySim sim;
+};
+
+#define B200_API extern "C" __attribute__((visibility("default")))
+
+#define B200_TRY(...)                                    \
+    try {                                                \
+        __VA_ARGS__;                                     \
+        return B200_OK;                                  \
+    } catch (const b200::CudaError& e) {                 \
+        b200::set_error(e.msg);                          \
+        return B200_ERR_CUDA;                            \
+    } catch (const std::exception& e) {                  \
+        b200::set_error(e.what());                       \
+        return B200_ERR_STATE;                           \
+    }
+
+#define B200_ARG(cond, text)                             \
+    if (!(cond)) {                                       \
+        b200::set_error(text);                           \
+        return B200_ERR_ARG;                             \
+    }
+
+B200_API const char* b200_last_error(void) { return b200::g_last_error.c_str(); }
+
+B200_API int b200_device_count(int* count)
+{
+    B200_ARG(count, "count is null");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        b200::set_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+        return B200_ERR_CUDA;
+    }
+    return B200_OK;
+}
+
+B200_API int b200_device_info(int device, char* name, int name_len)
+{
+    B200_ARG(name && name_len > 0, "name buffer is null");
+    B200_TRY({
+        cudaDeviceProp p;
+        B200_CHECK(cudaGetDeviceProperties(&p, device));
+        snprintf(name, (size_t)name_len, "%s (CC %d.%d, %dGB)", p.name, p.major, p.minor,
+                 (int)(p.totalGlobalMem >> 30));
+    })
+}
+
+B200_API int b200_nbody_create(int64_t n, const double* pos, const double* vel, const double* mass, double G,
+                               double softening, double damping, double theta, int device, b200_nbody** out)
+{
+    B200_ARG(out, "out handle is null");
+    *out = nullptr;
+    B200_ARG(n >= 0 && n < (int64_t)1 << 30, "n out of range [0, 2^30)");
+    B200_ARG(n == 0 || (pos && vel && mass), "pos/vel/mass is null");
+    B200_ARG(theta >= 0.0, "theta must be >= 0");
+    b200_nbody* h = new b200_nbody();
+    try {
+        h->sim.device = device;
+        h->sim.G = G;
+        h->sim.softening = softening;
+        h->sim.damping = damping;
+        h->sim.theta = theta;
+        b200::nbody_alloc(h->sim, (int)n);
+        b200::nbody_upload(h->sim, pos, vel, mass);
+    } catch (const b200::CudaError& e) {
+        b200::set_error(e.msg);
+        b200::nbody_free(h->sim);
+        delete h;
+        return B200_ERR_CUDA;
+    }
+    *out = h;
+    return B200_OK;
+}
+
+B200_API int b200_nbody_destroy(b200_nbody* h)
+{
+    if (!h) return B200_OK;
+    b200::nbody_free(h->sim);
+    delete h;
+    return B200_OK;
+}
+
+B200_API int b200_nbody_step(b200_nbody* h, double dt)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY(b200::nbody_step(h->sim, dt))
+}
+
+B200_API int b200_nbody_step_n(b200_nbody* h, double dt, int nsteps)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY({
+        for (int i = 0; i < nsteps; ++i) b200::nbody_step(h->sim, dt);
+    })
+}
+
+B200_API int b200_nbody_compute_accelerations(b200_nbody* h, float* out)
+{
+    B200_ARG(h && (out || h->sim.n == 0), "null argument");
+    B200_TRY(b200::nbody_get_accelerations(h->sim, out))
+}
+
+B200_API int b200_nbody_compute_colors(b200_nbody* h, double max_speed)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY(b200::nbody_compute_colors(h->sim, max_speed))
+}
+
+B200_API int b200_nbody_get_positions(b200_nbody* h, float* out)
+{
+    B200_ARG(h && (out || h->sim.n == 0), "null argument");
+    B200_TRY(b200::nbody_get_positions(h->sim, out))
+}
+
+B200_API int b200_nbody_get_positions_f64(b200_nbody* h, double* out)
+{
+    B200_ARG(h && (out || h->sim.n == 0), "null argument");
+    B200_TRY(b200::nbody_get_positions_f64(h->sim, out))
+}
+
+B200_API int b200_nbody_get_velocities(b200_nbody* h, double* out)
+{
+    B200_ARG(h && (out || h->sim.n == 0), "null argument");
+    B200_TRY(b200::nbody_get_velocities(h->sim, out))
+}
+
+B200_API int b200_nbody_get_colors(b200_nbody* h, float* out)
+{
+    B200_ARG(h && (out || h->sim.n == 0), "null argument");
+    B200_TRY(b200::nbody_get_colors(h->sim, out))
+}
+
+B200_API int b200_nbody_sync(b200_nbody* h)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY({
+        B200_CHECK(cudaSetDevice(h->sim.device));
+        B200_CHECK(cudaStreamSynchronize(h->sim.stream));
+    })
+}
+
+B200_API int b200_nbody_set_state(b200_nbody* h, const double* pos, const double* vel)
+{
+    B200_ARG(h && ((pos && vel) || h->sim.n == 0), "null argument");
+    B200_TRY(b200::nbody_upload_state(h->sim, pos, vel))
+}
+
+B200_API int b200_nbody_set_params(b200_nbody* h, double G, double softening, double damping, double theta)
+{
+    B200_ARG(h, "handle is null");
+    B200_ARG(theta >= 0.0, "theta must be >= 0");
+    h->sim.G = G;
+    h->sim.softening = softening;
+    h->sim.damping = damping;
+    h->sim.theta = theta;
+    h->sim.tree_valid = false;
+    return B200_OK;
+}
+
+B200_API int b200_nbody_get_keys(b200_nbody* h, uint64_t* out)
+{
+    B200_ARG(h && (out || h->sim.n == 0), "null argument");
+    B200_TRY(b200::nbody_get_keys(h->sim, out))
+}
+
+B200_API int b200_nbody_get_perm(b200_nbody* h, uint32_t* out)
+{
+    B200_ARG(h && (out || h->sim.n == 0), "null argument");
+    B200_TRY(b200::nbody_get_perm(h->sim, out))
+}
+
+B200_API int b200_nbody_get_stats(b200_nbody* h, b200_nbody_stats* out)
+{
+    B200_ARG(h && out, "null argument");
+    B200_TRY({
+        b200::NBodySim& s = h->sim;
+        B200_CHECK(cudaSetDevice(s.device));
+        B200_CHECK(cudaStreamSynchronize(s.stream));
+        memset(out, 0, sizeof(*out));
+        out->n = s.n;
+        out->steps = s.steps;
+        unsigned alloc = 0, err = 0;
+        unsigned long long inter = 0;
+        B200_CHECK(cudaMemcpy(&alloc, s.d_alloc, sizeof(alloc), cudaMemcpyDeviceToHost));
+        B200_CHECK(cudaMemcpy(&err, s.d_error, sizeof(err), cudaMemcpyDeviceToHost));
+        B200_CHECK(cudaMemcpy(&inter, s.d_interactions, sizeof(inter), cudaMemcpyDeviceToHost));
+        B200_CHECK(cudaMemcpy(&out->bounds, s.d_bounds, sizeof(double), cudaMemcpyDeviceToHost));
+        out->records = s.n > 1 ? (int64_t)alloc : s.n;
+        out->interactions = (int64_t)inter;
+        out->error_flags = err;
+        out->sm_count = s.sm_count;
+        out->bytes_allocated = (int64_t)s.bytes_allocated;
+        out->timed_steps = s.timer.count;
+        for (int i = 0; i < B200_NBODY_PHASES; ++i) out->phase_ms[i] = s.timer.ms[i];
+    })
+}
+
+B200_API int b200_nbody_reset_stats(b200_nbody* h)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY({
+        b200::NBodySim& s = h->sim;
+        B200_CHECK(cudaSetDevice(s.device));
+        B200_CHECK(cudaStreamSynchronize(s.stream));
+        B200_CHECK(cudaMemset(s.d_interactions, 0, sizeof(unsigned long long)));
+        s.timer.reset();
+    })
+}
+
+B200_API int b200_nbody_set_profiling(b200_nbody* h, int enabled)
+{
+    B200_ARG(h, "handle is null");
+    h->sim.timer.enabled = enabled != 0;
+    return B200_OK;
+}

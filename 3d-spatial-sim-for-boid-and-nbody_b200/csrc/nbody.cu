@@ -1,0 +1,733 @@
+// nbody.cu -- Barnes-Hut step on sm_100a: bounds, Morton keys, radix sort, LBVH + octree
+// records, warp-cooperative theta-MAC traversal, fused integrate.  See nbody.cuh for the layout.
+#include "nbody.cuh"
+
+namespace b200 {
+
+// ============================================================================ bounds
+// max |coord| over all bodies (nbody/simulation.py:308-317).  Non-negative doubles order
+// like their bit patterns, so the cross-block reduce is an integer atomicMax.
+__global__ void __launch_bounds__(256) absmax_kernel(const double* __restrict__ pos, int64_t count,
+                                                     unsigned long long* __restrict__ out)
+{
+    double m = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) m = fmax(m, fabs(pos[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ double wm[8];
+    if (lane_id() == 0) wm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? wm[threadIdx.x] : 0.0;
+        for (int o = 4; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+// ============================================================================ Morton keys
+// The key is the octant path the reference's insertion descent takes for this body through
+// 21 levels of the cube [-bounds, bounds]^3, with the reference's own fp64 arithmetic:
+// octant bit = (p >= c) (nbody/simulation.py:38-49), child centre = c +- half/2 level by
+// level (:52-60).  bounds = fma(max|coord|, 1.1, 10) (:317; numba fastmath contracts it).
+__global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ pos, int n,
+                                                     const unsigned long long* __restrict__ maxabs_bits,
+                                                     uint64_t* __restrict__ keys, double* __restrict__ bounds_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double bounds = __fma_rn(__longlong_as_double((long long)*maxabs_bits), 1.1, 10.0);
+    if (i == 0) *bounds_out = bounds;
+    if (i >= n) return;
+    const double px = pos[3 * (int64_t)i], py = pos[3 * (int64_t)i + 1], pz = pos[3 * (int64_t)i + 2];
+    double cx = 0.0, cy = 0.0, cz = 0.0, hs = bounds;
+    uint64_t k = 0;
+#pragma unroll
+    for (int l = 0; l < MORTON_LEVELS; ++l) {
+        const double q = hs * 0.5;
+        const bool bx = px >= cx, by = py >= cy, bz = pz >= cz;
+        k = (k << 3) | (uint64_t)((bx ? 1 : 0) | (by ? 2 : 0) | (bz ? 4 : 0));
+        cx = bx ? __dadd_rn(cx, q) : __dsub_rn(cx, q);
+        cy = by ? __dadd_rn(cy, q) : __dsub_rn(cy, q);
+        cz = bz ? __dadd_rn(cz, q) : __dsub_rn(cz, q);
+        hs = q;
+    }
+    keys[i] = k;
+}
+
+// ============================================================================ gather
+// Physically reorder the master state into the new Morton order (nearly the identity after
+// the first step, so the reads stay close to coalesced) and emit the float4 view.
+__global__ void __launch_bounds__(256) gather_kernel(const uint32_t* __restrict__ perm,
+                                                     const double* __restrict__ pos_in, const double* __restrict__ vel_in,
+                                                     const double* __restrict__ mass_in, const uint32_t* __restrict__ id_in,
+                                                     double* __restrict__ pos_out, double* __restrict__ vel_out,
+                                                     double* __restrict__ mass_out, uint32_t* __restrict__ id_out,
+                                                     float4* __restrict__ posm, int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t j = perm[k];
+    const double x = pos_in[3 * j], y = pos_in[3 * j + 1], z = pos_in[3 * j + 2];
+    const double vx = vel_in[3 * j], vy = vel_in[3 * j + 1], vz = vel_in[3 * j + 2];
+    const double m = mass_in[j];
+    const int64_t o = 3 * (int64_t)k;
+    pos_out[o] = x; pos_out[o + 1] = y; pos_out[o + 2] = z;
+    vel_out[o] = vx; vel_out[o + 1] = vy; vel_out[o + 2] = vz;
+    mass_out[k] = m;
+    id_out[k] = id_in[j];
+    posm[k] = make_float4((float)x, (float)y, (float)z, (float)m);
+}
+
+// ============================================================================ LBVH build
+// Common-prefix metric between sorted keys i and i+1 (larger = more similar); equal keys are
+// disambiguated by index (Karras 2012), which makes every metric inside a node's range
+// strictly larger than the two at its boundary.
+__device__ __forceinline__ int cpl(const uint64_t* __restrict__ keys, int i, int n)
+{
+    if (i < 0 || i >= n - 1) return -1;
+    const uint64_t x = keys[i] ^ keys[i + 1];
+    if (x) return __clzll((long long)x);                       // 1..63 (bit 63 of a key is 0)
+    return 64 + __clz((int)((unsigned)i ^ (unsigned)(i + 1)));  // 64..95
+}
+// Octree level of the smallest cell containing a node whose metric is c:
+// common prefix = c-1 bits = floor((c-1)/3) whole octant digits; >= 21 => one finest cell.
+__device__ __forceinline__ int level_of(int c)
+{
+    const int l = (c - 1) / 3;
+    return l > MORTON_LEVELS ? MORTON_LEVELS : l;
+}
+
+__device__ __forceinline__ D4 ldcg_d4(const D4* p)
+{
+    const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
+    const double2 b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    return D4{a.x, a.y, b.x, b.y};
+}
+
+// Bottom-up agglomerative construction (Apetrei 2014) of the Karras binary radix tree with
+// the mass / centre-of-mass reduction fused in: every leaf climbs; at each parent the first
+// arriver leaves its range end in other[] and stops, the second combines both children.
+// Internal node p sits at the split between sorted positions p and p+1.
+// Sums are carried as (sum m x, sum m y, sum m z, sum m) in fp64, the bottom-up equivalent
+// of the reference's running mean (nbody/simulation.py:160-167).
+__global__ void __launch_bounds__(256) build_kernel(const uint64_t* __restrict__ keys, const double* __restrict__ pos,
+                                                    const double* __restrict__ mass, int n,
+                                                    int* childL, int* childR, int* parent, int* other, int2* range,
+                                                    D4* msum, int* root)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double m = mass[k];
+    D4 S{m * pos[3 * (int64_t)k], m * pos[3 * (int64_t)k + 1], m * pos[3 * (int64_t)k + 2], m};
+    int l = k, r = k, node = ~k;
+    for (;;) {
+        if (l == 0 && r == n - 1) {
+            *root = node;
+            if (node >= 0) parent[node] = -1;
+            break;
+        }
+        const bool right = cpl(keys, r, n) > cpl(keys, l - 1, n);
+        const int p = right ? r : l - 1;
+        if (right) childL[p] = node; else childR[p] = node;
+        if (node >= 0) parent[node] = p;
+        __threadfence();
+        const int o = atomicExch(&other[p], right ? l : r);
+        if (o == -1) break;
+        __threadfence();
+        const int sib = __ldcg(right ? &childR[p] : &childL[p]);
+        D4 T;
+        if (sib >= 0) T = ldcg_d4(&msum[sib]);
+        else {
+            const int64_t kk = ~sib;
+            const double mm = mass[kk];
+            T = D4{mm * pos[3 * kk], mm * pos[3 * kk + 1], mm * pos[3 * kk + 2], mm};
+        }
+        // left + right, so the sum does not depend on which child arrived first
+        if (right) S = D4{S.x + T.x, S.y + T.y, S.z + T.z, S.w + T.w};
+        else       S = D4{T.x + S.x, T.y + S.y, T.z + S.z, T.w + S.w};
+        if (right) r = o; else l = o;
+        msum[p] = S;
+        range[p] = make_int2(l, r);
+        node = p;
+    }
+}
+
+// ---------------------------------------------------------------------------- octree records
+// A binary node is an octree cell ("head") iff its level differs from its parent's; binary
+// nodes with the parent's level are sub-octant groupings and are flattened away.  This is the
+// reference's octree with single-child chains collapsed to their deepest cell, whose size is
+// the one that decides the reference's MAC (all chain cells share mass and COM).
+template <typename F>
+__device__ __forceinline__ void for_each_octree_child(const uint64_t* __restrict__ keys, int n, const int* __restrict__ childL,
+                                                      const int* __restrict__ childR, const int2* __restrict__ range,
+                                                      int i, int Li, F&& emit)
+{
+    if (Li >= MORTON_LEVELS) {   // every body below shares one finest-level cell: bucket of leaves
+        const int2 rg = range[i];
+        for (int k = rg.x; k <= rg.y; ++k) emit(~k);
+        return;
+    }
+    int stack[8];
+    int sp = 0;
+    stack[sp++] = childR[i];
+    stack[sp++] = childL[i];
+    while (sp > 0) {
+        const int c = stack[--sp];
+        if (c >= 0 && level_of(cpl(keys, c, n)) == Li) {
+            stack[sp++] = childR[c];
+            stack[sp++] = childL[c];
+        } else {
+            emit(c);   // in key order == octant order
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) count_children_kernel(const uint64_t* __restrict__ keys, int n,
+                                                             const int* __restrict__ childL, const int* __restrict__ childR,
+                                                             const int* __restrict__ parent, const int2* __restrict__ range,
+                                                             int* __restrict__ first, int* __restrict__ nchild,
+                                                             unsigned* alloc, unsigned capacity, unsigned* error)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int Li = level_of(cpl(keys, i, n));
+    const int par = parent[i];
+    const bool head = par < 0 || level_of(cpl(keys, par, n)) != Li;
+    if (!head) { nchild[i] = 0; first[i] = -1; return; }
+    int cnt = 0;
+    for_each_octree_child(keys, n, childL, childR, range, i, Li, [&](int) { ++cnt; });
+    const unsigned f = atomicAdd(alloc, (unsigned)cnt);
+    if (f + (unsigned)cnt > capacity) { atomicOr(error, (unsigned)ERR_RECORD_OVERFLOW); nchild[i] = 0; first[i] = -1; return; }
+    nchild[i] = cnt;
+    first[i] = (int)f;
+}
+
+__device__ __forceinline__ void write_cell_record(float4* __restrict__ recs, int slot, const D4& S, int level, double bounds,
+                                                  double theta, int first, int nchild)
+{
+    const double inv = S.w > 0.0 ? 1.0 / S.w : 0.0;
+    // cell size = 2*bounds / 2^level; MAC  size/d < theta  <=>  d^2 > size^2/theta^2
+    const double size = ldexp(2.0 * bounds, -level);
+    const float thr = theta > 0.0 ? (float)((size * size) / (theta * theta)) : __int_as_float(0x7f800000);
+    recs[2 * (int64_t)slot] = make_float4((float)(S.x * inv), (float)(S.y * inv), (float)(S.z * inv), (float)S.w);
+    recs[2 * (int64_t)slot + 1] = make_float4(thr, __int_as_float(first), __int_as_float(nchild), __int_as_float(-1));
+}
+
+__global__ void __launch_bounds__(256) write_records_kernel(const uint64_t* __restrict__ keys, int n,
+                                                            const int* __restrict__ childL, const int* __restrict__ childR,
+                                                            const int* __restrict__ parent, const int2* __restrict__ range,
+                                                            const D4* __restrict__ msum, const int* __restrict__ first,
+                                                            const int* __restrict__ nchild, const float4* __restrict__ posm,
+                                                            const double* __restrict__ bounds_p, double theta,
+                                                            const int* __restrict__ root, float4* __restrict__ recs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int nc = nchild[i];
+    if (nc == 0) return;
+    const double bounds = *bounds_p;
+    const int Li = level_of(cpl(keys, i, n));
+    if (i == *root) write_cell_record(recs, 0, msum[i], Li, bounds, theta, first[i], nc);
+    int slot = first[i];
+    for_each_octree_child(keys, n, childL, childR, range, i, Li, [&](int c) {
+        if (c < 0) {
+            const int k = ~c;
+            recs[2 * (int64_t)slot] = posm[k];
+            recs[2 * (int64_t)slot + 1] = make_float4(-1.0f, __int_as_float(0), __int_as_float(0), __int_as_float(k));
+        } else {
+            write_cell_record(recs, slot, msum[c], level_of(cpl(keys, c, n)), bounds, theta, first[c], nchild[c]);
+        }
+        ++slot;
+    });
+}
+
+// single body: the root record is that leaf
+__global__ void single_body_record_kernel(const float4* __restrict__ posm, float4* __restrict__ recs)
+{
+    recs[0] = posm[0];
+    recs[1] = make_float4(-1.0f, __int_as_float(0), __int_as_float(0), __int_as_float(0));
+}
+
+// ============================================================================ traversal
+// One warp owns 32 consecutive sorted bodies (one per lane).  The warp walks the octree with
+// a shared stack in shared memory whose entries are (child block, lane mask): only cells that
+// some lane must OPEN are pushed, with the mask of exactly those lanes, so every lane makes
+// the reference's own per-body MAC decision (nbody/simulation.py:256-258) -- no group MAC.
+// Opening a cell loads its contiguous child records with one coalesced 16 B/lane load into a
+// per-warp staging buffer; each child is then evaluated by all lanes from a shared-memory
+// broadcast:  d2 = |com - p|^2 + eps^2;  accept iff d2 > size^2/theta^2 (leaf: always);
+// accepted and d2 > eps^2 (:260, also excludes the body itself): a += m (com - p) d2^-3/2.
+__global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const float4* __restrict__ recs, const float4* __restrict__ posm,
+                                                              float4* __restrict__ acc, int tile_begin, int tile_end, int n,
+                                                              float eps2, float G, unsigned* tile_counter,
+                                                              unsigned long long* interactions, unsigned* error)
+{
+    __shared__ uint4 s_stack[TRAV_WARPS][TRAV_STACK];
+    __shared__ float4 s_stage[TRAV_WARPS][2 * TRAV_STAGE];
+    const unsigned lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    uint4* stack = s_stack[warp];
+    float4* stage = s_stage[warp];
+    unsigned long long wcount = 0;
+
+    for (;;) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        const int tile = tile_begin + (int)t;
+        if (tile >= tile_end) break;
+        const int k = tile * 32 + (int)lane;
+        const bool valid = k < n;
+        const float4 p = valid ? posm[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        int cnt = 0;
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        int sp = 0;
+        if (lane == 0) stack[0] = make_uint4(0u, 1u, vmask, 0u);
+        sp = 1;
+        __syncwarp();
+        while (sp > 0) {
+            const uint4 e = stack[--sp];
+            const int first = (int)e.x, nch = (int)e.y;
+            const bool in = (e.z >> lane) & 1u;
+            for (int base = 0; base < nch; base += TRAV_STAGE) {
+                const int cn = min(TRAV_STAGE, nch - base);
+                __syncwarp();
+                if ((int)lane < 2 * cn) stage[lane] = __ldg(&recs[2 * (int64_t)(first + base) + lane]);
+                __syncwarp();
+                for (int c = 0; c < cn; ++c) {
+                    const float4 A = stage[2 * c];
+                    const float4 B = stage[2 * c + 1];
+                    const float dx = A.x - p.x, dy = A.y - p.y, dz = A.z - p.z;
+                    const float d2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, eps2)));
+                    const bool accept = d2 > B.x;
+                    const unsigned om = __ballot_sync(0xffffffffu, in && !accept);
+                    if (in && accept && d2 > eps2) {
+                        const float rinv = rsqrtf(d2);
+                        const float f = A.w * rinv * rinv * rinv;
+                        ax = fmaf(dx, f, ax);
+                        ay = fmaf(dy, f, ay);
+                        az = fmaf(dz, f, az);
+                        ++cnt;
+                    }
+                    if (om) {
+                        if (sp >= TRAV_STACK) {   // cannot happen for a 21-level tree; never drop silently
+                            if (lane == 0) atomicOr(error, (unsigned)ERR_STACK_OVERFLOW);
+                        } else {
+                            if (lane == 0) stack[sp] = make_uint4(__float_as_uint(B.y), __float_as_uint(B.z), om, 0u);
+                            ++sp;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (valid) acc[k] = make_float4(G * ax, G * ay, G * az, __int_as_float(cnt));
+        unsigned c32 = (unsigned)cnt;
+        for (int o = 16; o > 0; o >>= 1) c32 += __shfl_xor_sync(0xffffffffu, c32, o);
+        wcount += c32;
+    }
+    if (lane == 0 && wcount) atomicAdd(interactions, wcount);
+}
+
+// ============================================================================ integrate
+// v = (v + a dt) * damping; x += v dt (nbody/simulation.py:281-305; CUDA twin
+// gpu_backend.py:242-257), fp64 state, with the next step's max|coord| reduce fused in.
+__global__ void __launch_bounds__(256) integrate_kernel(double* __restrict__ pos, double* __restrict__ vel,
+                                                        const float4* __restrict__ acc, int n, double dt, double damping,
+                                                        unsigned long long* __restrict__ maxabs_out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    double m = 0.0;
+    if (k < n) {
+        const float4 a = acc[k];
+        const int64_t o = 3 * (int64_t)k;
+        const double a3[3] = {(double)a.x, (double)a.y, (double)a.z};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double v = vel[o + d];
+            v += a3[d] * dt;
+            v *= damping;
+            vel[o + d] = v;
+            const double x = pos[o + d] + v * dt;
+            pos[o + d] = x;
+            m = fmax(m, fabs(x));
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ double wm[8];
+    if (lane_id() == 0) wm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < 8 ? wm[threadIdx.x] : 0.0;
+        for (int o = 4; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0) atomicMax(maxabs_out, (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+// ============================================================================ colours / egress
+// speed -> RGB heat map (nbody/simulation.py:320-400; gpu_backend.py:259-325), written in
+// creation order through id[].
+__device__ __forceinline__ void speed_color(double t, float& r, float& g, float& b)
+{
+    double R, Gc, B;
+    if (t < 0.55) {
+        if (t < 0.15) { const double s = t / 0.15; R = 0.4 - 0.2 * s; Gc = 0.2 + 0.2 * s; B = 0.8 + 0.1 * s; }
+        else if (t < 0.30) { const double s = (t - 0.15) / 0.15; R = 0.2 + 0.1 * s; Gc = 0.4 + 0.1 * s; B = 0.9 + 0.05 * s; }
+        else {
+            const double s = (t - 0.30) / 0.25;
+            if (s < 0.6) { const double s2 = s / 0.6; R = 0.3 - 0.1 * s2; Gc = 0.5 + 0.3 * s2; B = 0.95 + 0.05 * s2; }
+            else { const double s2 = (s - 0.6) / 0.4; R = 0.2 + 0.8 * s2; Gc = 0.8 + 0.2 * s2; B = 1.0; }
+        }
+    } else if (t < 0.90) { R = 1.0; Gc = 1.0; B = 1.0; }
+    else if (t < 0.95) { const double s = (t - 0.90) / 0.05; R = 1.0; Gc = 1.0 - 0.05 * s; B = 1.0 - 1.0 * s; }
+    else if (t < 0.99) { const double s = (t - 0.95) / 0.04; R = 1.0; Gc = 0.95 - 0.45 * s; B = 0.0; }
+    else { const double s = (t - 0.99) / 0.01; R = 1.0; Gc = 0.5 - 0.5 * s; B = 0.0; }
+    r = (float)R; g = (float)Gc; b = (float)B;
+}
+
+__global__ void __launch_bounds__(256) colors_kernel(const double* __restrict__ vel, const uint32_t* __restrict__ id,
+                                                     float* __restrict__ colors, int n, double max_speed)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t o = 3 * (int64_t)k;
+    const double vx = vel[o], vy = vel[o + 1], vz = vel[o + 2];
+    const double speed = sqrt(vx * vx + vy * vy + vz * vz);
+    const double t = fmin(1.0, speed / max_speed);
+    float r, g, b;
+    speed_color(t, r, g, b);
+    const int64_t w = 3 * (int64_t)id[k];
+    colors[w] = r; colors[w + 1] = g; colors[w + 2] = b;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) unpermute3_kernel(const double* __restrict__ src, const uint32_t* __restrict__ id,
+                                                         T* __restrict__ dst, int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t o = 3 * (int64_t)k, w = 3 * (int64_t)id[k];
+    dst[w] = (T)src[o]; dst[w + 1] = (T)src[o + 1]; dst[w + 2] = (T)src[o + 2];
+}
+
+__global__ void __launch_bounds__(256) unpermute_acc_kernel(const float4* __restrict__ acc, const uint32_t* __restrict__ id,
+                                                            float* __restrict__ dst, int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float4 a = acc[k];
+    const int64_t w = 3 * (int64_t)id[k];
+    dst[w] = a.x; dst[w + 1] = a.y; dst[w + 2] = a.z;
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(uint32_t* __restrict__ p, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) scatter_mass_kernel(const double* __restrict__ mass_in, const uint32_t* __restrict__ id,
+                                                           double* __restrict__ mass_out, int n)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) mass_out[id[k]] = mass_in[k];
+}
+
+// ============================================================================ host side
+template <typename T>
+static T* alloc_counted(NBodySim& s, size_t count)
+{
+    s.bytes_allocated += (count ? count : 1) * sizeof(T);
+    return dev_alloc<T>(count);
+}
+
+void nbody_alloc(NBodySim& s, int n)
+{
+    s.n = n;
+    B200_CHECK(cudaSetDevice(s.device));
+    cudaDeviceProp prop;
+    B200_CHECK(cudaGetDeviceProperties(&prop, s.device));
+    s.sm_count = prop.multiProcessorCount;
+    B200_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    const size_t N = (size_t)n;
+    for (int b = 0; b < 2; ++b) {
+        s.pos[b] = alloc_counted<double>(s, 3 * N);
+        s.vel[b] = alloc_counted<double>(s, 3 * N);
+        s.mass[b] = alloc_counted<double>(s, N);
+        s.id[b] = alloc_counted<uint32_t>(s, N);
+        s.keys[b] = alloc_counted<uint64_t>(s, N);
+        s.vals[b] = alloc_counted<uint32_t>(s, N);
+    }
+    s.sorter.init(n);
+    s.bytes_allocated += s.sorter.bytes();
+    s.posm = alloc_counted<float4>(s, N);
+    s.acc = alloc_counted<float4>(s, N);
+    s.childL = alloc_counted<int>(s, N);
+    s.childR = alloc_counted<int>(s, N);
+    s.parent = alloc_counted<int>(s, N);
+    s.other = alloc_counted<int>(s, N);
+    s.range = alloc_counted<int2>(s, N);
+    s.msum = alloc_counted<D4>(s, N);
+    s.first = alloc_counted<int>(s, N);
+    s.nchild = alloc_counted<int>(s, N);
+    s.rec_capacity = 2 * (int64_t)N + 2;   // root + N leaves + <= N-1 cells
+    s.recs = alloc_counted<float4>(s, 2 * (size_t)s.rec_capacity);
+    s.colors = alloc_counted<float>(s, 3 * N);
+    s.stage = alloc_counted<double>(s, 3 * N);
+    s.d_maxabs = alloc_counted<unsigned long long>(s, 2);
+    s.d_bounds = alloc_counted<double>(s, 1);
+    s.d_root = alloc_counted<int>(s, 1);
+    s.d_alloc = alloc_counted<unsigned>(s, 1);
+    s.d_tile_counter = alloc_counted<unsigned>(s, 1);
+    s.d_interactions = alloc_counted<unsigned long long>(s, 1);
+    s.d_error = alloc_counted<unsigned>(s, 1);
+    B200_CHECK(cudaMemset(s.d_error, 0, sizeof(unsigned)));
+    B200_CHECK(cudaMemset(s.d_interactions, 0, sizeof(unsigned long long)));
+    B200_CHECK(cudaMemset(s.colors, 0, 3 * N * sizeof(float)));
+    s.shard_begin = 0;
+    s.shard_end = n;
+    s.timer.init();
+}
+
+void nbody_free(NBodySim& s)
+{
+    cudaSetDevice(s.device);
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(s.pos[b]); cudaFree(s.vel[b]); cudaFree(s.mass[b]); cudaFree(s.id[b]);
+        cudaFree(s.keys[b]); cudaFree(s.vals[b]);
+    }
+    s.sorter.destroy();
+    cudaFree(s.posm); cudaFree(s.acc); cudaFree(s.childL); cudaFree(s.childR); cudaFree(s.parent);
+    cudaFree(s.other); cudaFree(s.range); cudaFree(s.msum); cudaFree(s.first); cudaFree(s.nchild);
+    cudaFree(s.recs); cudaFree(s.colors); cudaFree(s.stage); cudaFree(s.d_maxabs); cudaFree(s.d_bounds);
+    cudaFree(s.d_root); cudaFree(s.d_alloc); cudaFree(s.d_tile_counter); cudaFree(s.d_interactions);
+    cudaFree(s.d_error);
+    s.timer.destroy();
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s.stream = nullptr;
+}
+
+static void recompute_maxabs(NBodySim& s)
+{
+    s.maxabs_slot = 0;
+    B200_CHECK(cudaMemsetAsync(s.d_maxabs, 0, 2 * sizeof(unsigned long long), s.stream));
+    if (s.n > 0) {
+        const int64_t count = 3 * (int64_t)s.n;
+        const int64_t want = (count + 255) / 256, cap = (int64_t)s.sm_count * 16;
+        const int blocks = (int)(want < cap ? want : cap);
+        absmax_kernel<<<blocks, 256, 0, s.stream>>>(s.pos[s.cur], count, s.d_maxabs);
+        B200_CHECK(cudaGetLastError());
+    }
+}
+
+void nbody_upload(NBodySim& s, const double* pos, const double* vel, const double* mass)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    const size_t N = (size_t)s.n;
+    s.cur = 0;
+    B200_CHECK(cudaMemcpyAsync(s.pos[0], pos, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    B200_CHECK(cudaMemcpyAsync(s.vel[0], vel, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    B200_CHECK(cudaMemcpyAsync(s.mass[0], mass, N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    if (s.n > 0) iota_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.id[0], s.n);
+    recompute_maxabs(s);
+    s.tree_valid = false;
+    B200_CHECK(cudaStreamSynchronize(s.stream));
+}
+
+// New positions / velocities for the same bodies, given in creation order.
+void nbody_upload_state(NBodySim& s, const double* pos, const double* vel)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    const size_t N = (size_t)s.n;
+    // bring masses back to creation order alongside: simplest is to scatter through id[]
+    // into the other buffer, then continue from there with id = iota.
+    const int o = s.cur ^ 1;
+    B200_CHECK(cudaMemcpyAsync(s.pos[o], pos, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    B200_CHECK(cudaMemcpyAsync(s.vel[o], vel, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    if (s.n > 0) {
+        scatter_mass_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.mass[s.cur], s.id[s.cur], s.mass[o], s.n);
+        iota_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.id[o], s.n);
+    }
+    s.cur = o;
+    recompute_maxabs(s);
+    s.tree_valid = false;
+    B200_CHECK(cudaStreamSynchronize(s.stream));
+}
+
+void nbody_build_tree(NBodySim& s)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    const int n = s.n;
+    if (n == 0) { s.tree_valid = true; return; }
+    const int grid = div_up(n, 256);
+    cudaStream_t st = s.stream;
+    s.timer.begin(st);
+    // ---- keys
+    keygen_kernel<<<grid, 256, 0, st>>>(s.pos[s.cur], n, s.d_maxabs + s.maxabs_slot, s.keys[0], s.d_bounds);
+    B200_CHECK(cudaGetLastError());
+    s.timer.mark(st);
+    // ---- sort (key, position)
+    s.sorted_slot = s.sorter.sort(s.keys, s.vals, 0, n, 0, 64, /*iota=*/true, st, s.sm_count);
+    s.timer.mark(st);
+    // ---- physical reorder
+    const int o = s.cur ^ 1;
+    gather_kernel<<<grid, 256, 0, st>>>(s.vals[s.sorted_slot], s.pos[s.cur], s.vel[s.cur], s.mass[s.cur], s.id[s.cur],
+                                        s.pos[o], s.vel[o], s.mass[o], s.id[o], s.posm, n);
+    B200_CHECK(cudaGetLastError());
+    s.cur = o;
+    s.timer.mark(st);
+    // ---- binary radix tree + mass/COM
+    if (n > 1) {
+        B200_CHECK(cudaMemsetAsync(s.other, 0xff, (size_t)n * sizeof(int), st));
+        build_kernel<<<grid, 256, 0, st>>>(s.keys[s.sorted_slot], s.pos[s.cur], s.mass[s.cur], n, s.childL, s.childR,
+                                           s.parent, s.other, s.range, s.msum, s.d_root);
+        B200_CHECK(cudaGetLastError());
+    }
+    s.timer.mark(st);
+    // ---- octree records
+    if (n > 1) {
+        const unsigned one = 1u;   // record 0 is the root
+        B200_CHECK(cudaMemcpyAsync(s.d_alloc, &one, sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        const int g1 = div_up(n - 1, 256);
+        count_children_kernel<<<g1, 256, 0, st>>>(s.keys[s.sorted_slot], n, s.childL, s.childR, s.parent, s.range, s.first,
+                                                  s.nchild, s.d_alloc, (unsigned)s.rec_capacity, s.d_error);
+        write_records_kernel<<<g1, 256, 0, st>>>(s.keys[s.sorted_slot], n, s.childL, s.childR, s.parent, s.range, s.msum,
+                                                 s.first, s.nchild, s.posm, s.d_bounds, s.theta, s.d_root, s.recs);
+    } else {
+        single_body_record_kernel<<<1, 1, 0, st>>>(s.posm, s.recs);
+    }
+    B200_CHECK(cudaGetLastError());
+    s.timer.mark(st);
+    s.tree_valid = true;
+}
+
+void nbody_traverse(NBodySim& s, int begin, int end)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    cudaStream_t st = s.stream;
+    if (end > begin) {
+        B200_REQUIRE(begin % 32 == 0, "traversal range must start on a 32-body tile");
+        const int tile_begin = begin / 32, tile_end = div_up(end, 32);
+        B200_CHECK(cudaMemsetAsync(s.d_tile_counter, 0, sizeof(unsigned), st));
+        const int tiles = tile_end - tile_begin;
+        const int max_blocks = s.sm_count * 6;
+        const int blocks = min(div_up(tiles, TRAV_WARPS), max_blocks);
+        const float eps2 = (float)(s.softening * s.softening);
+        traverse_kernel<<<blocks, TRAV_BLOCK, 0, st>>>(s.recs, s.posm, s.acc, tile_begin, tile_end, min(end, s.n), eps2,
+                                                       (float)s.G, s.d_tile_counter, s.d_interactions, s.d_error);
+        B200_CHECK(cudaGetLastError());
+    }
+    s.timer.mark(st);
+}
+
+void nbody_integrate(NBodySim& s, double dt)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    cudaStream_t st = s.stream;
+    if (s.n > 0) {
+        const int next = s.maxabs_slot ^ 1;
+        B200_CHECK(cudaMemsetAsync(s.d_maxabs + next, 0, sizeof(unsigned long long), st));
+        integrate_kernel<<<div_up(s.n, 256), 256, 0, st>>>(s.pos[s.cur], s.vel[s.cur], s.acc, s.n, dt, s.damping,
+                                                           s.d_maxabs + next);
+        B200_CHECK(cudaGetLastError());
+        s.maxabs_slot = next;
+    }
+    s.timer.mark(st);
+    s.tree_valid = false;
+    ++s.steps;
+}
+
+void nbody_step(NBodySim& s, double dt)
+{
+    nbody_build_tree(s);
+    nbody_traverse(s, 0, s.n);
+    s.timer.mark(s.stream);   // exchange phase: empty on one GPU
+    nbody_integrate(s, dt);
+    if (s.timer.enabled) {
+        B200_CHECK(cudaStreamSynchronize(s.stream));
+        s.timer.collect();
+    }
+}
+
+void nbody_compute_colors(NBodySim& s, double max_speed)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    if (s.n > 0) {
+        colors_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.vel[s.cur], s.id[s.cur], s.colors, s.n, max_speed);
+        B200_CHECK(cudaGetLastError());
+    }
+}
+
+void nbody_get_positions(NBodySim& s, float* out)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    if (s.n == 0) return;
+    unpermute3_kernel<float><<<div_up(s.n, 256), 256, 0, s.stream>>>(s.pos[s.cur], s.id[s.cur], (float*)s.stage, s.n);
+    B200_CHECK(cudaGetLastError());
+    B200_CHECK(cudaMemcpyAsync(out, s.stage, 3 * (size_t)s.n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    B200_CHECK(cudaStreamSynchronize(s.stream));
+}
+
+void nbody_get_positions_f64(NBodySim& s, double* out)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    if (s.n == 0) return;
+    unpermute3_kernel<double><<<div_up(s.n, 256), 256, 0, s.stream>>>(s.pos[s.cur], s.id[s.cur], (double*)s.stage, s.n);
+    B200_CHECK(cudaGetLastError());
+    B200_CHECK(cudaMemcpyAsync(out, s.stage, 3 * (size_t)s.n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    B200_CHECK(cudaStreamSynchronize(s.stream));
+}
+
+void nbody_get_velocities(NBodySim& s, double* out)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    if (s.n == 0) return;
+    unpermute3_kernel<double><<<div_up(s.n, 256), 256, 0, s.stream>>>(s.vel[s.cur], s.id[s.cur], (double*)s.stage, s.n);
+    B200_CHECK(cudaGetLastError());
+    B200_CHECK(cudaMemcpyAsync(out, s.stage, 3 * (size_t)s.n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    B200_CHECK(cudaStreamSynchronize(s.stream));
+}
+
+void nbody_get_colors(NBodySim& s, float* out)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    if (s.n == 0) return;
+    B200_CHECK(cudaMemcpyAsync(out, s.colors, 3 * (size_t)s.n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    B200_CHECK(cudaStreamSynchronize(s.stream));
+}
+
+void nbody_get_accelerations(NBodySim& s, float* out)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    if (s.n == 0) return;
+    const bool timing = s.timer.enabled;
+    s.timer.enabled = false;
+    if (!s.tree_valid) nbody_build_tree(s);
+    nbody_traverse(s, 0, s.n);
+    s.timer.enabled = timing;
+    unpermute_acc_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.acc, s.id[s.cur], (float*)s.stage, s.n);
+    B200_CHECK(cudaGetLastError());
+    B200_CHECK(cudaMemcpyAsync(out, s.stage, 3 * (size_t)s.n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    B200_CHECK(cudaStreamSynchronize(s.stream));
+}
+
+void nbody_get_keys(NBodySim& s, uint64_t* out)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    if (s.n == 0) return;
+    if (!s.tree_valid) nbody_build_tree(s);
+    B200_CHECK(cudaMemcpyAsync(out, s.keys[s.sorted_slot], (size_t)s.n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
+    B200_CHECK(cudaStreamSynchronize(s.stream));
+}
+
+void nbody_get_perm(NBodySim& s, uint32_t* out)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    if (s.n == 0) return;
+    if (!s.tree_valid) nbody_build_tree(s);
+    B200_CHECK(cudaMemcpyAsync(out, s.id[s.cur], (size_t)s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+    B200_CHECK(cudaStreamSynchronize(s.stream));
+}
+
+}  // namespace b200

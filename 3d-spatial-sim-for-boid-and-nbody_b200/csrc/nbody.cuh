@@ -1,0 +1,108 @@
+// nbody.cuh -- device state and kernels of the Barnes-Hut step (sm_100a).
+//
+// Replaces, on device, the reference's per-substep sequence (tools/record.py:835-858):
+//   compute_bounds (nbody/simulation.py:308-317) -> build_octree (:63-198) ->
+//   compute_forces_barnes_hut (:201-278) -> update_positions_velocities (:281-305)
+// and compute_colors_by_velocity (:320-400).
+//
+// Data layout in HBM (N bodies):
+//   state[2]   double-buffered master state in the CURRENT Morton order:
+//                pos (N,3) f64, vel (N,3) f64, mass (N) f64, id (N) u32 = creation index
+//   keys[2]/vals[2]  63-bit Morton keys + permutation, radix-sort ping-pong
+//   posm       (N) float4 {x,y,z,m} of the sorted bodies (traversal targets / leaf records)
+//   binary radix tree over the sorted keys (N-1 internal nodes): childL/childR/parent,
+//                range, msum = (sum m x, sum m y, sum m z, sum m) in f64
+//   recs       octree records, 32 B each = 2 x float4:
+//                A = {com.x, com.y, com.z, mass}
+//                B = {open_threshold = size^2/theta^2 (leaf: -1), first_child, nchild, body}
+//              children of a cell are CONTIGUOUS records, so opening a cell is one
+//              coalesced 16-byte-per-lane load.
+//   acc        (N) float4 {ax, ay, az, interaction count} in sorted order
+#pragma once
+#include "common.cuh"
+#include "radix_sort.cuh"
+
+namespace b200 {
+
+struct __align__(16) D4 { double x, y, z, w; };
+
+constexpr int MORTON_LEVELS = 21;
+constexpr int TRAV_BLOCK = 256;
+constexpr int TRAV_WARPS = TRAV_BLOCK / 32;
+constexpr int TRAV_STACK = 160;      // >= 1 + 7 * 21: only cells that must be opened are pushed
+constexpr int TRAV_STAGE = 16;       // records staged per chunk (32 lanes x 16 B)
+
+enum NBodyPhase { PH_KEYGEN = 0, PH_SORT, PH_GATHER, PH_BUILD, PH_EXTRACT, PH_TRAVERSE, PH_EXCHANGE, PH_INTEGRATE, PH_COUNT };
+
+enum NBodyError { ERR_STACK_OVERFLOW = 1, ERR_RECORD_OVERFLOW = 2 };
+
+struct NBodySim {
+    int n = 0;
+    int device = 0;
+    int sm_count = 148;
+    double G = 0, softening = 0, damping = 1, theta = 0.5;
+    cudaStream_t stream = nullptr;
+
+    double* pos[2] = {nullptr, nullptr};
+    double* vel[2] = {nullptr, nullptr};
+    double* mass[2] = {nullptr, nullptr};
+    uint32_t* id[2] = {nullptr, nullptr};
+    int cur = 0;
+
+    uint64_t* keys[2] = {nullptr, nullptr};
+    uint32_t* vals[2] = {nullptr, nullptr};
+    int sorted_slot = 0;             // which keys/vals slot holds the last sort's output
+    rsort::Sorter<uint64_t> sorter;
+
+    float4* posm = nullptr;
+    float4* acc = nullptr;
+    int *childL = nullptr, *childR = nullptr, *parent = nullptr, *other = nullptr;
+    int2* range = nullptr;
+    D4* msum = nullptr;
+    int *first = nullptr, *nchild = nullptr;
+    float4* recs = nullptr;
+    int64_t rec_capacity = 0;
+
+    // small device scalars
+    unsigned long long* d_maxabs = nullptr;   // [2] bit patterns of max |coord|
+    int maxabs_slot = 0;
+    double* d_bounds = nullptr;
+    int* d_root = nullptr;
+    unsigned* d_alloc = nullptr;              // record allocator
+    unsigned* d_tile_counter = nullptr;
+    unsigned long long* d_interactions = nullptr;
+    unsigned* d_error = nullptr;
+
+    float* colors = nullptr;                  // (N,3) f32, creation order
+    void* stage = nullptr;                    // (N,3) f64-sized staging for getters
+    bool tree_valid = false;                  // keys/perm/tree describe the current positions
+
+    // multi-GPU: this rank traverses sorted bodies [shard_begin, shard_end) (multiples of 32)
+    int rank = 0, world = 1;
+    int shard_begin = 0, shard_end = 0;
+
+    PhaseTimer timer;
+    int64_t steps = 0;
+    size_t bytes_allocated = 0;
+};
+
+void nbody_alloc(NBodySim& s, int n);
+void nbody_free(NBodySim& s);
+void nbody_upload(NBodySim& s, const double* pos, const double* vel, const double* mass);
+void nbody_upload_state(NBodySim& s, const double* pos, const double* vel);
+// keygen .. extract: leaves keys/perm/tree valid for the current positions
+void nbody_build_tree(NBodySim& s);
+// traversal of sorted bodies [begin, end) into s.acc
+void nbody_traverse(NBodySim& s, int begin, int end);
+void nbody_integrate(NBodySim& s, double dt);
+void nbody_step(NBodySim& s, double dt);
+void nbody_compute_colors(NBodySim& s, double max_speed);
+void nbody_get_positions(NBodySim& s, float* out);
+void nbody_get_positions_f64(NBodySim& s, double* out);
+void nbody_get_velocities(NBodySim& s, double* out);
+void nbody_get_colors(NBodySim& s, float* out);
+void nbody_get_accelerations(NBodySim& s, float* out);   // creation order, runs build+traverse if needed
+void nbody_get_keys(NBodySim& s, uint64_t* out);
+void nbody_get_perm(NBodySim& s, uint32_t* out);
+
+}  // namespace b200

@@ -1,0 +1,236 @@
+"""Drop-in replacement for the reference's ``nbody/gpu_backend.py`` on NVIDIA B200.
+
+Same module-level names and call contracts as the reference (nbody/gpu_backend.py):
+``Backend`` (:29-33), ``detect_backend`` (:36-55), ``get_backend`` (:119-125),
+``force_backend`` (:128-132), ``create_gpu_simulation`` (:623-679), ``CUDA_THRESHOLD`` (:618),
+and a simulation object with the reference's duck type (``CUDASimulation`` :336-409):
+``step(dt)``, ``compute_colors(max_speed)``, ``get_positions()`` -> (n,3) float32 in creation
+order, ``get_velocities()`` -> (n,3) float64, ``get_colors()`` -> (n,3) float32, ``sync()``,
+attributes ``n, G, softening, damping`` (+ ``theta`` like the Metal Barnes-Hut twin).
+
+Unlike the reference's CUDA class (an fp64 O(n^2) sum) the device step IS Barnes-Hut with
+the reference CPU path's semantics (nbody/simulation.py:63-305): see csrc/nbody.cu.
+Callers (tools/record.py:759-784, nbody/simulation.py:509-540) run unchanged.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from enum import Enum
+from typing import Optional, Tuple
+
+import numpy as np
+
+from .. import _lib
+
+
+class Backend(Enum):  # nbody/gpu_backend.py:29-33 (same members and values)
+    CUDA = "cuda"
+    METAL_BH = "metal_barnes_hut"
+    METAL = "metal"
+    CPU = "cpu"
+
+
+def _check_cuda() -> Tuple[bool, str]:
+    """nbody/gpu_backend.py:58-70, through the C ABI instead of numba.cuda."""
+    if _lib.device_count() > 0:
+        return True, _lib.device_info(0)
+    return False, ""
+
+
+def _get_cpu_info() -> str:  # nbody/gpu_backend.py:103-111
+    import multiprocessing
+    import platform
+    try:
+        return f"{platform.processor()} ({multiprocessing.cpu_count()} cores)"
+    except Exception:
+        return platform.processor() or "Unknown CPU"
+
+
+def detect_backend() -> Tuple[Backend, str]:
+    ok, info = _check_cuda()
+    if ok:
+        return Backend.CUDA, info
+    return Backend.CPU, _get_cpu_info()
+
+
+_BACKEND: Optional[Backend] = None
+_BACKEND_INFO: str = ""
+
+
+def get_backend() -> Tuple[Backend, str]:
+    """Cached detection (nbody/gpu_backend.py:119-125)."""
+    global _BACKEND, _BACKEND_INFO
+    if _BACKEND is None:
+        _BACKEND, _BACKEND_INFO = detect_backend()
+        print(f"[GPU] Using backend: {_BACKEND.value} - {_BACKEND_INFO}")
+    return _BACKEND, _BACKEND_INFO
+
+
+def force_backend(backend: Backend):
+    """nbody/gpu_backend.py:128-132"""
+    global _BACKEND, _BACKEND_INFO
+    _BACKEND = backend
+    _BACKEND_INFO = f"Forced: {backend.value}"
+
+
+def _as_f64(a, shape_tail):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.ndim != len(shape_tail) + 1 or tuple(a.shape[1:]) != tuple(shape_tail):
+        raise ValueError(f"expected array of shape (n,{','.join(map(str, shape_tail))}), got {a.shape}")
+    return a
+
+
+class B200BarnesHutSimulation:
+    """Device-resident Barnes-Hut simulation (duck type of CUDASimulation, gpu_backend.py:336-409)."""
+
+    def __init__(self, positions: np.ndarray, velocities: np.ndarray, masses: np.ndarray,
+                 G: float, softening: float, damping: float, theta: float = 0.5, device: int = 0):
+        L = _lib.load()
+        pos = _as_f64(positions, (3,))
+        vel = _as_f64(velocities, (3,))
+        mass = _as_f64(masses, ())
+        if not (len(pos) == len(vel) == len(mass)):
+            raise ValueError("positions, velocities and masses disagree on n")
+        self.n = len(pos)
+        self.G = float(G)
+        self.softening = float(softening)
+        self.damping = float(damping)
+        self.theta = float(theta)
+        self.device = int(device)
+        self._L = L
+        self._h = C.c_void_p()
+        dp = C.POINTER(C.c_double)
+        _lib.check(L.b200_nbody_create(self.n, pos.ctypes.data_as(dp), vel.ctypes.data_as(dp),
+                                       mass.ctypes.data_as(dp), self.G, self.softening, self.damping,
+                                       self.theta, self.device, C.byref(self._h)))
+        print(f"[CUDA] Initialized with {self.n:,} bodies")
+        print(f"[CUDA] Using B200 Barnes-Hut kernel (theta={self.theta})")
+
+    # ---- reference duck type -------------------------------------------------------------
+    def step(self, dt: float):
+        """One force evaluation + kick-drift (gpu_backend.py:368-386; semantics of
+        tools/record.py:835-858).  Asynchronous."""
+        _lib.check(self._L.b200_nbody_step(self._handle(), float(dt)))
+
+    def compute_colors(self, max_speed: float):
+        _lib.check(self._L.b200_nbody_compute_colors(self._handle(), float(max_speed)))
+
+    def get_positions(self) -> np.ndarray:
+        out = np.empty((self.n, 3), np.float32)
+        _lib.check(self._L.b200_nbody_get_positions(self._handle(), out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def get_velocities(self) -> np.ndarray:
+        out = np.empty((self.n, 3), np.float64)
+        _lib.check(self._L.b200_nbody_get_velocities(self._handle(), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def get_colors(self) -> np.ndarray:
+        out = np.empty((self.n, 3), np.float32)
+        _lib.check(self._L.b200_nbody_get_colors(self._handle(), out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def sync(self):
+        _lib.check(self._L.b200_nbody_sync(self._handle()))
+
+    # ---- additions for parity tests and measurement ------------------
+    def step_n(self, dt: float, nsteps: int):
+        _lib.check(self._L.b200_nbody_step_n(self._handle(), float(dt), int(nsteps)))
+
+    def compute_accelerations(self) -> np.ndarray:
+        """Barnes-Hut accelerations of the current state, (n,3) float32, creation order; the
+        device twin of compute_forces_barnes_hut (nbody/simulation.py:201-278)."""
+        out = np.empty((self.n, 3), np.float32)
+        _lib.check(self._L.b200_nbody_compute_accelerations(self._handle(), out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def get_positions_f64(self) -> np.ndarray:
+        out = np.empty((self.n, 3), np.float64)
+        _lib.check(self._L.b200_nbody_get_positions_f64(self._handle(), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def get_morton_keys(self) -> np.ndarray:
+        out = np.empty(self.n, np.uint64)
+        _lib.check(self._L.b200_nbody_get_keys(self._handle(), out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def get_sort_permutation(self) -> np.ndarray:
+        out = np.empty(self.n, np.uint32)
+        _lib.check(self._L.b200_nbody_get_perm(self._handle(), out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
+    def set_state(self, positions: np.ndarray, velocities: np.ndarray):
+        pos, vel = _as_f64(positions, (3,)), _as_f64(velocities, (3,))
+        if len(pos) != self.n or len(vel) != self.n:
+            raise ValueError("set_state: n differs from the simulation's")
+        dp = C.POINTER(C.c_double)
+        _lib.check(self._L.b200_nbody_set_state(self._handle(), pos.ctypes.data_as(dp), vel.ctypes.data_as(dp)))
+
+    def set_params(self, G=None, softening=None, damping=None, theta=None):
+        self.G = self.G if G is None else float(G)
+        self.softening = self.softening if softening is None else float(softening)
+        self.damping = self.damping if damping is None else float(damping)
+        self.theta = self.theta if theta is None else float(theta)
+        _lib.check(self._L.b200_nbody_set_params(self._handle(), self.G, self.softening, self.damping, self.theta))
+
+    def set_profiling(self, enabled: bool):
+        _lib.check(self._L.b200_nbody_set_profiling(self._handle(), int(bool(enabled))))
+
+    def reset_stats(self):
+        _lib.check(self._L.b200_nbody_reset_stats(self._handle()))
+
+    def get_stats(self) -> dict:
+        st = _lib.NBodyStats()
+        _lib.check(self._L.b200_nbody_get_stats(self._handle(), C.byref(st)))
+        d = {k: getattr(st, k) for k, _ in st._fields_ if k != "phase_ms"}
+        d["phase_ms"] = {name: st.phase_ms[i] for i, name in enumerate(_lib.PHASE_NAMES)}
+        if st.error_flags:
+            raise _lib.B200Error(f"device error flags {st.error_flags:#x} (1 = traversal stack overflow, "
+                                 "2 = octree record pool overflow)")
+        return d
+
+    # ---- lifetime --------------------------------------------------------------------------
+    def _handle(self):
+        if not self._h:
+            raise _lib.B200Error("simulation is closed")
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b200_nbody_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+CUDASimulation = B200BarnesHutSimulation  # the name the reference's CUDA path exports
+
+# nbody/gpu_backend.py:618.  The reference caps its O(n^2) CUDA class at 100 000 bodies unless
+# force_gpu; the Barnes-Hut device step has no such crossover, the name is kept for importers.
+CUDA_THRESHOLD = 1 << 30
+METAL_BH_THRESHOLD = 2_000_000
+METAL_THRESHOLD = 5_000
+
+
+def create_gpu_simulation(positions: np.ndarray, velocities: np.ndarray, masses: np.ndarray,
+                          G: float, softening: float, damping: float, theta: float = 0.5,
+                          force_gpu: bool = False):
+    """Factory with the reference's signature and None-means-CPU contract
+    (nbody/gpu_backend.py:623-679)."""
+    backend, _info = get_backend()
+    n = len(positions)
+    if backend == Backend.CUDA:
+        if n <= CUDA_THRESHOLD or force_gpu:
+            return B200BarnesHutSimulation(positions, velocities, masses, G, softening, damping, theta)
+        return None
+    return None  # CPU: the caller's own Barnes-Hut path (the reference's, not this package's)

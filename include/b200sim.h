@@ -1,0 +1,91 @@
+/*
+ * b200sim.h -- C ABI of libb200sim.so: the B200-native (sm_100a) Barnes-Hut step and boids
+ * neighbour-rule update behind the reference's backend interface.
+ *
+ * Plain pointers and sizes only.  Every function returns 0 on success and a non-zero status
+ * on failure; b200_last_error() then returns a message (thread-local).  Host pointers are
+ * ordinary (pageable or pinned) host memory; arrays are C-contiguous.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository):
+ *   nbody/gpu_backend.py:336-409   class CUDASimulation (step / compute_colors / get_* / sync)
+ *   nbody/gpu_backend.py:623-679   create_gpu_simulation(...)
+ *   nbody/simulation.py:201-218    compute_forces_barnes_hut(...)  (the CPU "force entry point")
+ *   tools/record.py:835-858        the CPU substep sequence the device step replaces
+ *   boids/flock.py:627-678         Flock.update(dt)
+ */
+#ifndef B200SIM_H
+#define B200SIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_CUDA 1
+#define B200_ERR_ARG 2
+#define B200_ERR_STATE 3
+
+typedef struct b200_nbody b200_nbody;   /* opaque handle */
+typedef struct b200_boids b200_boids;   /* opaque handle */
+
+/* Per-phase device time of step(), accumulated while profiling is on (CUDA events). */
+#define B200_NBODY_PHASES 8
+/* order: keygen, sort, gather, build, extract, traverse, exchange, integrate */
+
+typedef struct b200_nbody_stats {
+    int64_t n;                 /* bodies */
+    int64_t steps;             /* step() calls so far */
+    int64_t records;           /* octree records of the last tree: root + cells + leaves */
+    int64_t interactions;      /* accepted body-node interactions since the last reset (device-counted) */
+    double  bounds;            /* root half-size of the last tree: fma(max|coord|, 1.1, 10) */
+    uint32_t error_flags;      /* 0 = clean; 1 = traversal stack overflow; 2 = record pool overflow */
+    int32_t  sm_count;
+    int64_t bytes_allocated;   /* device bytes owned by the handle */
+    int64_t timed_steps;       /* steps accumulated in phase_ms */
+    double  phase_ms[B200_NBODY_PHASES];
+} b200_nbody_stats;
+
+const char* b200_last_error(void);
+int b200_device_count(int* count);
+/* name buffer receives "<name> (CC x.y, N GB)" like nbody/gpu_backend.py:58-70 prints */
+int b200_device_info(int device, char* name, int name_len);
+
+/* ---- n-body ------------------------------------------------------------------------------
+ * create: replaces CUDASimulation.__init__ (nbody/gpu_backend.py:339-366) + theta of the
+ * Metal Barnes-Hut twin.  Copies pos (n,3), vel (n,3), mass (n) [fp64] to the device. */
+int b200_nbody_create(int64_t n, const double* pos, const double* vel, const double* mass,
+                      double G, double softening, double damping, double theta,
+                      int device, b200_nbody** out);
+int b200_nbody_destroy(b200_nbody* h);
+/* step: replaces CUDASimulation.step (nbody/gpu_backend.py:368-386): one force evaluation +
+ * kick-drift.  Asynchronous with respect to the host. */
+int b200_nbody_step(b200_nbody* h, double dt);
+int b200_nbody_step_n(b200_nbody* h, double dt, int nsteps);
+/* Barnes-Hut accelerations of the current state, creation order, (n,3) fp32, no integrate:
+ * the device twin of compute_forces_barnes_hut (nbody/simulation.py:201-278). */
+int b200_nbody_compute_accelerations(b200_nbody* h, float* out);
+/* compute_colors / get_* / sync: nbody/gpu_backend.py:388-409.  get_* return creation order. */
+int b200_nbody_compute_colors(b200_nbody* h, double max_speed);
+int b200_nbody_get_positions(b200_nbody* h, float* out);     /* (n,3) fp32 */
+int b200_nbody_get_positions_f64(b200_nbody* h, double* out);/* (n,3) fp64 master state */
+int b200_nbody_get_velocities(b200_nbody* h, double* out);   /* (n,3) fp64 */
+int b200_nbody_get_colors(b200_nbody* h, float* out);        /* (n,3) fp32 */
+int b200_nbody_sync(b200_nbody* h);
+/* Replace positions and velocities (creation order, fp64) keeping masses: the restore path
+ * of tools/record.py:718-735 without rebuilding the object. */
+int b200_nbody_set_state(b200_nbody* h, const double* pos, const double* vel);
+int b200_nbody_set_params(b200_nbody* h, double G, double softening, double damping, double theta);
+/* Sorted 63-bit Morton keys of the current state and the sort permutation
+ * (perm[k] = creation index of the body at sorted position k). */
+int b200_nbody_get_keys(b200_nbody* h, uint64_t* out);
+int b200_nbody_get_perm(b200_nbody* h, uint32_t* out);
+int b200_nbody_get_stats(b200_nbody* h, b200_nbody_stats* out);
+int b200_nbody_reset_stats(b200_nbody* h);
+int b200_nbody_set_profiling(b200_nbody* h, int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SIM_H */

@@ -1,0 +1,221 @@
+"""Parity of the CUDA Barnes-Hut path (through the C ABI) against the CPU oracle.  -m gpu."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as orc  # noqa: E402
+
+
+def _sim(pos, vel, mass, G, eps, damping=1.0, theta=0.5):
+    from b200sim.nbody.gpu_backend import B200BarnesHutSimulation
+    return B200BarnesHutSimulation(pos, vel, mass, G, eps, damping, theta)
+
+
+def _rms_rel(a, ref):
+    return float(np.sqrt(((a - ref) ** 2).sum() / (ref ** 2).sum()))
+
+
+def _golden(golden_dir, name):
+    return np.load(os.path.join(golden_dir, f"nbody_{name}.npz"))
+
+
+GOLDEN = ["galaxy_2k", "collision_3k", "cluster_2k"]
+# tolerance stated by BASELINE.json north_star / SURVEY.md section 8c
+ACC_RMS_TOL = 1e-4
+
+
+@pytest.mark.parametrize("case", GOLDEN)
+def test_keys_and_permutation_bit_exact_golden(golden_dir, case):
+    g = _golden(golden_dir, case)
+    sim = _sim(g["pos"], g["vel"], g["mass"], float(g["G"]), float(g["softening"]))
+    keys = orc.morton_keys(g["pos"], float(g["bounds"]))
+    perm = orc.sort_permutation(keys)
+    assert np.array_equal(sim.get_morton_keys(), keys[perm])
+    assert np.array_equal(sim.get_sort_permutation(), perm)
+    st = sim.get_stats()
+    assert st["bounds"] == float(g["bounds"])
+
+
+@pytest.mark.parametrize("case", GOLDEN)
+def test_accelerations_match_reference_golden(golden_dir, case):
+    g = _golden(golden_dir, case)
+    for th in g["thetas"]:
+        sim = _sim(g["pos"], g["vel"], g["mass"], float(g["G"]), float(g["softening"]), theta=float(th))
+        acc = sim.compute_accelerations().astype(np.float64)
+        ref = g[f"acc_theta_{th}"]
+        assert _rms_rel(acc, ref) <= ACC_RMS_TOL, (case, th, _rms_rel(acc, ref))
+
+
+@pytest.mark.parametrize("case", GOLDEN)
+def test_two_steps_and_colours_match_reference_golden(golden_dir, case):
+    g = _golden(golden_dir, case)
+    sim = _sim(g["pos"], g["vel"], g["mass"], float(g["G"]), float(g["softening"]),
+               damping=float(g["damping"]), theta=float(g["thetas"][0]))
+    sim.step(float(g["dt"]))
+    sim.step(float(g["dt"]))
+    sim.compute_colors(15.0)
+    pos, vel, col = sim.get_positions_f64(), sim.get_velocities(), sim.get_colors()
+    dv = g["vel_after2"] - g["vel"]
+    assert np.abs(vel - g["vel_after2"]).max() <= 2e-4 * np.abs(dv).max()
+    dp = g["pos_after2"] - g["pos"]
+    assert np.abs(pos - g["pos_after2"]).max() <= 2e-4 * np.abs(dp).max()
+    assert np.array_equal(sim.get_positions(), pos.astype(np.float32))
+    assert np.abs(col - g["colors_after2"]).max() < 1e-3   # same branch, fp32 speed differences
+    assert np.allclose(col, orc.colors(vel, 15.0), atol=2e-7)
+
+
+@pytest.mark.parametrize("dist,n,theta,seed", [("galaxy", 50_000, 0.95, 0), ("collision", 100_000, 0.5, 1),
+                                               ("cluster", 60_000, 0.7, 2), ("cluster", 20_000, 0.3, 3),
+                                               ("galaxy", 30_000, 1.5, 4)])
+def test_accelerations_match_oracle_synthetic(dist, n, theta, seed):
+    from b200sim import presets
+    R, G, eps = 500.0, 0.1, 2.0
+    pos, vel, mass = presets.generate(dist, n, R, G, seed)
+    rng = np.random.default_rng(seed)
+    mass = rng.uniform(0.5, 2.0, n)
+    sim = _sim(pos, vel, mass, G, eps, theta=theta)
+    acc = sim.compute_accelerations().astype(np.float64)
+    tree = orc.build_octree(pos, mass)
+    st = {}
+    ref = orc.compute_forces(pos, tree, theta, G, eps, stats=st)
+    assert _rms_rel(acc, ref) <= ACC_RMS_TOL
+    # per-body: all but (rare) borderline MAC flips within 1e-3
+    rel = np.linalg.norm(acc - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert (rel > 1e-3).mean() < 1e-3
+    # same tree and same interaction lists: cells with >= 2 children + leaves; accepted interactions
+    nn = tree.num_nodes
+    nkids = (tree.node_children[:nn] >= 0).sum(1)
+    expected_records = int((nkids >= 2).sum() + tree.node_is_leaf[:nn].sum())
+    gst = sim.get_stats()
+    assert gst["records"] == expected_records
+    assert abs(gst["interactions"] - st["interactions"]) <= 1e-4 * st["interactions"]
+    # keys/permutation at this size too
+    keys = orc.morton_keys(pos)
+    perm = orc.sort_permutation(keys)
+    assert np.array_equal(sim.get_morton_keys(), keys[perm])
+    assert np.array_equal(sim.get_sort_permutation(), perm)
+
+
+def test_theta_zero_is_direct_sum():
+    from b200sim import presets
+    n, G, eps = 4000, 0.1, 1.0
+    pos, vel, mass = presets.generate("cluster", n, 300.0, G, 5)
+    sim = _sim(pos, vel, mass, G, eps, theta=0.0)
+    acc = sim.compute_accelerations().astype(np.float64)
+    ref = orc.direct_sum(pos, mass, G, eps)
+    assert _rms_rel(acc, ref) <= 1e-5
+    assert sim.get_stats()["interactions"] == n * (n - 1)
+
+
+def test_error_vs_direct_sum_not_worse_than_reference():
+    from b200sim import presets
+    n, G, eps = 20_000, 0.05, 1.0
+    pos, vel, mass = presets.generate("cluster", n, 300.0, G, 1)
+    tgt = np.arange(0, n, 10)
+    direct = orc.direct_sum(pos, mass, G, eps, targets=tgt)
+    tree = orc.build_octree(pos, mass)
+    for th in (0.3, 0.5, 0.7, 0.9):
+        ref_err = _rms_rel(orc.compute_forces(pos, tree, th, G, eps, targets=tgt), direct)
+        acc = _sim(pos, vel, mass, G, eps, theta=th).compute_accelerations().astype(np.float64)[tgt]
+        assert _rms_rel(acc, direct) <= 1.05 * ref_err + 1e-6, th
+
+
+def test_two_body_analytic_and_cube_corners():
+    G, eps = 0.7, 0.25
+    pos = np.array([[-1.0, 0.5, 2.0], [3.0, -0.5, 1.0]])
+    mass = np.array([2.0, 5.0])
+    acc = _sim(pos, np.zeros((2, 3)), mass, G, eps).compute_accelerations().astype(np.float64)
+    d = pos[1] - pos[0]
+    r2 = d @ d + eps * eps
+    np.testing.assert_allclose(acc[0], G * mass[1] * d / r2 ** 1.5, rtol=2e-6)
+    np.testing.assert_allclose(acc[1], -G * mass[0] * d / r2 ** 1.5, rtol=2e-6)
+    corners = np.array([[x, y, z] for x in (-1.0, 1.0) for y in (-1.0, 1.0) for z in (-1.0, 1.0)] + [[0.0, 0.0, 0.0]])
+    acc = _sim(corners, np.zeros((9, 3)), np.ones(9), 1.0, 0.1, theta=0.0).compute_accelerations()
+    assert np.abs(acc[8]).max() < 1e-6
+    mags = np.linalg.norm(acc[:8], axis=1)
+    np.testing.assert_allclose(mags, mags[0], rtol=1e-5)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 31, 32, 33, 257])
+def test_small_and_ragged_sizes(n):
+    rng = np.random.default_rng(n)
+    pos = rng.normal(size=(n, 3)) * 50
+    vel = rng.normal(size=(n, 3))
+    mass = rng.uniform(0.5, 2, n)
+    sim = _sim(pos, vel, mass, 0.3, 0.5, theta=0.6)
+    acc = sim.compute_accelerations().astype(np.float64)
+    assert acc.shape == (n, 3)
+    if n >= 2:
+        tree = orc.build_octree(pos, mass)
+        ref = orc.compute_forces(pos, tree, 0.6, 0.3, 0.5)
+        assert _rms_rel(acc, ref) <= ACC_RMS_TOL
+    elif n == 1:
+        assert np.all(acc == 0)
+    sim.step(0.1)
+    sim.compute_colors(15.0)
+    assert sim.get_positions().shape == (n, 3) and sim.get_colors().shape == (n, 3)
+    if n:
+        p = pos.copy(); v = vel.copy()
+        orc.nbody_step(p, v, mass, 0.6, 0.3, 0.5, 1.0, 0.1)
+        np.testing.assert_allclose(sim.get_positions_f64(), p, rtol=1e-6, atol=1e-5)
+
+
+def test_coincident_bodies_and_degenerate_layouts():
+    """Collisions in the finest Morton cell: bodies at exactly the same point (the reference
+    would subdivide forever; the device groups them in a leaf bucket) and bodies on a line."""
+    rng = np.random.default_rng(11)
+    base = rng.normal(size=(500, 3)) * 20
+    pos = np.concatenate([base, base[:40], base[:40], np.zeros((70, 3))])
+    n = len(pos)
+    mass = rng.uniform(0.5, 2, n)
+    G, eps = 0.2, 0.3
+    sim = _sim(pos, np.zeros((n, 3)), mass, G, eps, theta=0.5)
+    acc = sim.compute_accelerations().astype(np.float64)
+    assert np.isfinite(acc).all()
+    # theta = 0 must still be the exact direct sum, duplicates included
+    acc0 = _sim(pos, np.zeros((n, 3)), mass, G, eps, theta=0.0).compute_accelerations().astype(np.float64)
+    assert _rms_rel(acc0, orc.direct_sum(pos, mass, G, eps)) <= 1e-5
+    # finite theta: close to the direct sum at BH accuracy
+    assert _rms_rel(acc, orc.direct_sum(pos, mass, G, eps)) < 5e-2
+    keys = orc.morton_keys(pos)
+    perm = orc.sort_permutation(keys)
+    assert np.array_equal(sim.get_morton_keys(), keys[perm])
+    assert np.array_equal(sim.get_sort_permutation(), perm)   # ties broken by creation index
+    line = np.zeros((300, 3)); line[:, 0] = np.linspace(-100, 100, 300)
+    m1 = np.ones(300)
+    acc = _sim(line, np.zeros((300, 3)), m1, 1.0, 0.5, theta=0.7).compute_accelerations().astype(np.float64)
+    ref = orc.compute_forces(line, orc.build_octree(line, m1), 0.7, 1.0, 0.5)
+    assert _rms_rel(acc, ref) <= ACC_RMS_TOL
+
+
+def test_set_state_and_creation_order_roundtrip():
+    from b200sim import presets
+    n = 10_000
+    pos, vel, mass = presets.generate("galaxy", n, 200.0, 0.2, 9)
+    mass = np.random.default_rng(0).uniform(0.5, 2.0, n)
+    sim = _sim(pos, vel, mass, 0.2, 5.0, theta=0.9)
+    assert np.array_equal(sim.get_positions_f64(), pos)
+    assert np.array_equal(sim.get_velocities(), vel)
+    a1 = sim.compute_accelerations()
+    assert np.array_equal(sim.get_positions_f64(), pos)      # re-sorting did not disturb creation order
+    for _ in range(3):
+        sim.step(0.1)
+    sim.set_state(pos, vel)                                   # masses must follow their bodies
+    a2 = sim.compute_accelerations()
+    assert np.array_equal(a1, a2)
+
+
+def test_many_steps_track_oracle_trajectory():
+    from b200sim import presets
+    cfg, pos, vel, mass = presets.generate_preset("tiny_galaxy", seed=0, num_bodies=5000)
+    sim = _sim(pos, vel, mass, cfg["G"], cfg["softening"], cfg["damping"], cfg["theta"])
+    p, v = pos.copy(), vel.copy()
+    for _ in range(10):
+        sim.step(cfg["dt"])
+        orc.nbody_step(p, v, mass, cfg["theta"], cfg["G"], cfg["softening"], cfg["damping"], cfg["dt"])
+    disp = np.abs(p - pos).max()
+    assert np.abs(sim.get_positions_f64() - p).max() <= 1e-4 * disp
+    assert sim.get_stats()["steps"] == 10
