@@ -22,6 +22,26 @@ class NBodyStats(C.Structure):
     ]
 
 
+N_BOIDS_PHASES = 5
+BOIDS_PHASE_NAMES = ("cells", "sort", "gather", "table", "rules")
+BOIDS_PARAM_FIELDS = ("bounds", "max_speed", "max_force", "wall_margin", "wall_weight", "perception_radius",
+                      "separation_radius", "separation_weight", "alignment_weight", "cohesion_weight",
+                      "color_blend_rate")
+
+
+class BoidsParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in BOIDS_PARAM_FIELDS]
+
+
+class BoidsStats(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64), ("steps", C.c_int64), ("num_cells", C.c_int64), ("grid_dim", C.c_int32),
+        ("key_bits", C.c_int32), ("cell_size", C.c_double), ("grid_offset", C.c_double),
+        ("neighbor_pairs", C.c_int64), ("bytes_allocated", C.c_int64), ("launches", C.c_int64),
+        ("timed_steps", C.c_int64), ("phase_ms", C.c_double * N_BOIDS_PHASES),
+    ]
+
+
 class B200Error(RuntimeError):
     """Raised for every non-zero status of the C ABI (callers of the reference backend catch
     Exception around construction: nbody/simulation.py:533-540, tools/record.py:781-784)."""
@@ -54,6 +74,25 @@ SIGNATURES = {
     "b200_nbody_get_stats": (C.c_int, [_h, C.POINTER(NBodyStats)]),
     "b200_nbody_reset_stats": (C.c_int, [_h]),
     "b200_nbody_set_profiling": (C.c_int, [_h, C.c_int]),
+    "b200_nbody_timed_steps": (C.c_int, [_h, C.c_double, C.c_int, C.POINTER(C.c_float)]),
+    "b200_nbody_launch_count": (C.c_int, [_h, C.POINTER(C.c_int64)]),
+    "b200_nbody_set_stream": (C.c_int, [_h, C.c_void_p, C.c_int]),
+    "b200_nbody_set_shard": (C.c_int, [_h, C.c_int64, C.c_int64]),
+    "b200_nbody_step_begin": (C.c_int, [_h]),
+    "b200_nbody_step_end": (C.c_int, [_h, C.c_double]),
+    "b200_nbody_acc_buffer": (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "b200_fp32_peak_tflops": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "b200_boids_create": (C.c_int, [C.c_int64, _dp, _dp, _dp, C.POINTER(BoidsParams), C.c_int, C.POINTER(_h)]),
+    "b200_boids_destroy": (C.c_int, [_h]),
+    "b200_boids_step": (C.c_int, [_h, C.c_double]),
+    "b200_boids_get_state": (C.c_int, [_h, _dp, _dp, _dp]),
+    "b200_boids_set_state": (C.c_int, [_h, _dp, _dp, _dp]),
+    "b200_boids_get_cell_indices": (C.c_int, [_h, C.POINTER(C.c_int32)]),
+    "b200_boids_get_stats": (C.c_int, [_h, C.POINTER(BoidsStats)]),
+    "b200_boids_reset_stats": (C.c_int, [_h]),
+    "b200_boids_set_profiling": (C.c_int, [_h, C.c_int]),
+    "b200_boids_timed_steps": (C.c_int, [_h, C.c_double, C.c_int, C.POINTER(C.c_float)]),
+    "b200_boids_sync": (C.c_int, [_h]),
 }
 
 _lib = None
@@ -98,3 +137,9 @@ def device_info(device: int = 0) -> str:
     buf = C.create_string_buffer(256)
     check(load().b200_device_info(device, buf, 256))
     return buf.value.decode()
+
+
+def fp32_peak_tflops(device: int = 0) -> float:
+    v = C.c_double(0.0)
+    check(load().b200_fp32_peak_tflops(device, C.byref(v)))
+    return float(v.value)

@@ -1,6 +1,7 @@
 // capi.cu -- extern "C" boundary of libb200sim.so (see include/b200sim.h).
 #include "../../include/b200sim.h"
 #include "nbody.cuh"
+#include "boids.cuh"
 
 #include <string.h>
 
@@ -12,6 +13,10 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 struct b200_nbody {
     b200::NBodySim sim;
 };
+struct b200_boids {
+    b200::BoidsSim sim;
+};
+static_assert(sizeof(b200_boids_params) == sizeof(b200::BoidsParams), "boids params layout");
 
 #define B200_API extern "C" __attribute__((visibility("default")))
 
@@ -227,4 +232,206 @@ B200_API int b200_nbody_set_profiling(b200_nbody* h, int enabled)
     B200_ARG(h, "handle is null");
     h->sim.timer.enabled = enabled != 0;
     return B200_OK;
+}
+
+B200_API int b200_nbody_timed_steps(b200_nbody* h, double dt, int nsteps, float* elapsed_ms)
+{
+    B200_ARG(h && elapsed_ms, "null argument");
+    B200_TRY({
+        b200::NBodySim& s = h->sim;
+        B200_CHECK(cudaSetDevice(s.device));
+        cudaEvent_t e0, e1;
+        B200_CHECK(cudaEventCreate(&e0));
+        B200_CHECK(cudaEventCreate(&e1));
+        B200_CHECK(cudaEventRecord(e0, s.stream));
+        for (int i = 0; i < nsteps; ++i) b200::nbody_step(s, dt);
+        B200_CHECK(cudaEventRecord(e1, s.stream));
+        B200_CHECK(cudaEventSynchronize(e1));
+        B200_CHECK(cudaEventElapsedTime(elapsed_ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    })
+}
+
+B200_API int b200_nbody_launch_count(b200_nbody* h, int64_t* out)
+{
+    B200_ARG(h && out, "null argument");
+    *out = h->sim.launches;
+    return B200_OK;
+}
+
+B200_API int b200_nbody_set_stream(b200_nbody* h, void* cuda_stream, int external)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY({
+        b200::NBodySim& s = h->sim;
+        B200_CHECK(cudaSetDevice(s.device));
+        B200_CHECK(cudaStreamSynchronize(s.stream));
+        s.stream = external ? (cudaStream_t)cuda_stream : s.own_stream;
+    })
+}
+
+B200_API int b200_nbody_set_shard(b200_nbody* h, int64_t begin, int64_t end)
+{
+    B200_ARG(h, "handle is null");
+    B200_ARG(begin >= 0 && begin <= end && end <= h->sim.n && (begin % 32 == 0 || begin == end), "bad shard range");
+    h->sim.shard_begin = (int)begin;
+    h->sim.shard_end = (int)end;
+    return B200_OK;
+}
+
+B200_API int b200_nbody_step_begin(b200_nbody* h)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY(b200::nbody_step_begin(h->sim))
+}
+
+B200_API int b200_nbody_step_end(b200_nbody* h, double dt)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY(b200::nbody_step_end(h->sim, dt))
+}
+
+B200_API int b200_nbody_acc_buffer(b200_nbody* h, void** device_ptr, int64_t* capacity_entries)
+{
+    B200_ARG(h && device_ptr && capacity_entries, "null argument");
+    *device_ptr = h->sim.acc;
+    *capacity_entries = h->sim.acc_capacity;
+    return B200_OK;
+}
+
+B200_API int b200_fp32_peak_tflops(int device, double* tflops)
+{
+    B200_ARG(tflops, "null argument");
+    B200_TRY(*tflops = b200::fp32_peak_tflops(device))
+}
+
+// ============================================================================ boids
+B200_API int b200_boids_create(int64_t n, const double* pos, const double* vel, const double* col,
+                               const b200_boids_params* params, int device, b200_boids** out)
+{
+    B200_ARG(out, "out handle is null");
+    *out = nullptr;
+    B200_ARG(params, "params is null");
+    B200_ARG(n >= 0 && n < (int64_t)1 << 30, "n out of range [0, 2^30)");
+    B200_ARG(n == 0 || (pos && vel && col), "pos/vel/col is null");
+    B200_ARG(params->perception_radius > 0 && params->bounds > 0 && params->wall_margin > 0, "bad boids params");
+    b200_boids* h = new b200_boids();
+    try {
+        h->sim.device = device;
+        memcpy(&h->sim.p, params, sizeof(b200::BoidsParams));
+        b200::boids_alloc(h->sim, (int)n);
+        b200::boids_upload(h->sim, pos, vel, col);
+    } catch (const b200::CudaError& e) {
+        b200::set_error(e.msg);
+        b200::boids_free(h->sim);
+        delete h;
+        return B200_ERR_CUDA;
+    }
+    *out = h;
+    return B200_OK;
+}
+
+B200_API int b200_boids_destroy(b200_boids* h)
+{
+    if (!h) return B200_OK;
+    b200::boids_free(h->sim);
+    delete h;
+    return B200_OK;
+}
+
+B200_API int b200_boids_step(b200_boids* h, double dt)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY(b200::boids_step(h->sim, dt))
+}
+
+B200_API int b200_boids_get_state(b200_boids* h, double* pos, double* vel, double* col)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY(b200::boids_get_state(h->sim, pos, vel, col))
+}
+
+B200_API int b200_boids_set_state(b200_boids* h, const double* pos, const double* vel, const double* col)
+{
+    B200_ARG(h && ((pos && vel && col) || h->sim.n == 0), "null argument");
+    B200_TRY(b200::boids_upload(h->sim, pos, vel, col))
+}
+
+B200_API int b200_boids_get_cell_indices(b200_boids* h, int32_t* out)
+{
+    B200_ARG(h && (out || h->sim.n == 0), "null argument");
+    B200_TRY(b200::boids_get_cells(h->sim, out))
+}
+
+B200_API int b200_boids_get_stats(b200_boids* h, b200_boids_stats* out)
+{
+    B200_ARG(h && out, "null argument");
+    B200_TRY({
+        b200::BoidsSim& s = h->sim;
+        B200_CHECK(cudaSetDevice(s.device));
+        B200_CHECK(cudaStreamSynchronize(s.stream));
+        memset(out, 0, sizeof(*out));
+        out->n = s.n;
+        out->steps = s.steps;
+        out->num_cells = s.num_cells;
+        out->grid_dim = s.grid_dim;
+        out->key_bits = s.key_bits;
+        out->cell_size = s.cell_size;
+        out->grid_offset = s.grid_offset;
+        unsigned long long pairs = 0;
+        B200_CHECK(cudaMemcpy(&pairs, s.d_pairs, sizeof(pairs), cudaMemcpyDeviceToHost));
+        out->neighbor_pairs = (int64_t)pairs;
+        out->bytes_allocated = (int64_t)s.bytes_allocated;
+        out->launches = s.launches;
+        out->timed_steps = s.timer.count;
+        for (int i = 0; i < B200_BOIDS_PHASES; ++i) out->phase_ms[i] = s.timer.ms[i];
+    })
+}
+
+B200_API int b200_boids_reset_stats(b200_boids* h)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY({
+        b200::BoidsSim& s = h->sim;
+        B200_CHECK(cudaSetDevice(s.device));
+        B200_CHECK(cudaStreamSynchronize(s.stream));
+        B200_CHECK(cudaMemset(s.d_pairs, 0, sizeof(unsigned long long)));
+        s.timer.reset();
+    })
+}
+
+B200_API int b200_boids_set_profiling(b200_boids* h, int enabled)
+{
+    B200_ARG(h, "handle is null");
+    h->sim.timer.enabled = enabled != 0;
+    return B200_OK;
+}
+
+B200_API int b200_boids_timed_steps(b200_boids* h, double dt, int nsteps, float* elapsed_ms)
+{
+    B200_ARG(h && elapsed_ms, "null argument");
+    B200_TRY({
+        b200::BoidsSim& s = h->sim;
+        B200_CHECK(cudaSetDevice(s.device));
+        cudaEvent_t e0, e1;
+        B200_CHECK(cudaEventCreate(&e0));
+        B200_CHECK(cudaEventCreate(&e1));
+        B200_CHECK(cudaEventRecord(e0, s.stream));
+        for (int i = 0; i < nsteps; ++i) b200::boids_step(s, dt);
+        B200_CHECK(cudaEventRecord(e1, s.stream));
+        B200_CHECK(cudaEventSynchronize(e1));
+        B200_CHECK(cudaEventElapsedTime(elapsed_ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    })
+}
+
+B200_API int b200_boids_sync(b200_boids* h)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY({
+        B200_CHECK(cudaSetDevice(h->sim.device));
+        B200_CHECK(cudaStreamSynchronize(h->sim.stream));
+    })
 }

@@ -188,17 +188,37 @@ __global__ void __launch_bounds__(256) count_children_kernel(const uint64_t* __r
                                                              unsigned* alloc, unsigned capacity, unsigned* error)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    const int Li = level_of(cpl(keys, i, n));
-    const int par = parent[i];
-    const bool head = par < 0 || level_of(cpl(keys, par, n)) != Li;
-    if (!head) { nchild[i] = 0; first[i] = -1; return; }
     int cnt = 0;
-    for_each_octree_child(keys, n, childL, childR, range, i, Li, [&](int) { ++cnt; });
-    const unsigned f = atomicAdd(alloc, (unsigned)cnt);
-    if (f + (unsigned)cnt > capacity) { atomicOr(error, (unsigned)ERR_RECORD_OVERFLOW); nchild[i] = 0; first[i] = -1; return; }
+    if (i < n - 1) {
+        const int Li = level_of(cpl(keys, i, n));
+        const int par = parent[i];
+        const bool head = par < 0 || level_of(cpl(keys, par, n)) != Li;
+        if (head) for_each_octree_child(keys, n, childL, childR, range, i, Li, [&](int) { ++cnt; });
+    }
+    // block-aggregated allocation of the child blocks: ONE atomic per CTA on the shared counter
+    // (a per-thread atomicAdd on one address serialises in L2: 21 ms at 50 M bodies).
+    __shared__ unsigned wsum[8];
+    __shared__ unsigned s_base;
+    unsigned inc = (unsigned)cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane_id() >= (unsigned)o) inc += t;
+    }
+    const int warp = threadIdx.x >> 5;
+    if (lane_id() == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int w = 0; w < 8; ++w) { const unsigned t = wsum[w]; wsum[w] = tot; tot += t; }
+        unsigned base = tot ? atomicAdd(alloc, tot) : 0u;
+        if (base + tot > capacity) { atomicOr(error, (unsigned)ERR_RECORD_OVERFLOW); base = 0xffffffffu; }
+        s_base = base;
+    }
+    __syncthreads();
+    if (i >= n - 1) return;
+    if (cnt == 0 || s_base == 0xffffffffu) { nchild[i] = 0; first[i] = -1; return; }
     nchild[i] = cnt;
-    first[i] = (int)f;
+    first[i] = (int)(s_base + wsum[warp] + inc - (unsigned)cnt);
 }
 
 __device__ __forceinline__ void write_cell_record(float4* __restrict__ recs, int slot, const D4& S, int level, double bounds,
@@ -448,7 +468,8 @@ void nbody_alloc(NBodySim& s, int n)
     cudaDeviceProp prop;
     B200_CHECK(cudaGetDeviceProperties(&prop, s.device));
     s.sm_count = prop.multiProcessorCount;
-    B200_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    B200_CHECK(cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking));
+    s.stream = s.own_stream;
     const size_t N = (size_t)n;
     for (int b = 0; b < 2; ++b) {
         s.pos[b] = alloc_counted<double>(s, 3 * N);
@@ -461,7 +482,8 @@ void nbody_alloc(NBodySim& s, int n)
     s.sorter.init(n);
     s.bytes_allocated += s.sorter.bytes();
     s.posm = alloc_counted<float4>(s, N);
-    s.acc = alloc_counted<float4>(s, N);
+    s.acc_capacity = (int64_t)N + 32 * 64;   // room for padded equal slices up to 64 ranks
+    s.acc = alloc_counted<float4>(s, (size_t)s.acc_capacity);
     s.childL = alloc_counted<int>(s, N);
     s.childR = alloc_counted<int>(s, N);
     s.parent = alloc_counted<int>(s, N);
@@ -504,7 +526,8 @@ void nbody_free(NBodySim& s)
     cudaFree(s.d_root); cudaFree(s.d_alloc); cudaFree(s.d_tile_counter); cudaFree(s.d_interactions);
     cudaFree(s.d_error);
     s.timer.destroy();
-    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.own_stream) cudaStreamDestroy(s.own_stream);
+    s.own_stream = nullptr;
     s.stream = nullptr;
 }
 
@@ -517,6 +540,7 @@ static void recompute_maxabs(NBodySim& s)
         const int64_t want = (count + 255) / 256, cap = (int64_t)s.sm_count * 16;
         const int blocks = (int)(want < cap ? want : cap);
         absmax_kernel<<<blocks, 256, 0, s.stream>>>(s.pos[s.cur], count, s.d_maxabs);
+        ++s.launches;
         B200_CHECK(cudaGetLastError());
     }
 }
@@ -565,15 +589,18 @@ void nbody_build_tree(NBodySim& s)
     s.timer.begin(st);
     // ---- keys
     keygen_kernel<<<grid, 256, 0, st>>>(s.pos[s.cur], n, s.d_maxabs + s.maxabs_slot, s.keys[0], s.d_bounds);
+    ++s.launches;
     B200_CHECK(cudaGetLastError());
     s.timer.mark(st);
     // ---- sort (key, position)
     s.sorted_slot = s.sorter.sort(s.keys, s.vals, 0, n, 0, 64, /*iota=*/true, st, s.sm_count);
+    s.launches += s.sorter.last_launches;
     s.timer.mark(st);
     // ---- physical reorder
     const int o = s.cur ^ 1;
     gather_kernel<<<grid, 256, 0, st>>>(s.vals[s.sorted_slot], s.pos[s.cur], s.vel[s.cur], s.mass[s.cur], s.id[s.cur],
                                         s.pos[o], s.vel[o], s.mass[o], s.id[o], s.posm, n);
+    ++s.launches;
     B200_CHECK(cudaGetLastError());
     s.cur = o;
     s.timer.mark(st);
@@ -582,6 +609,7 @@ void nbody_build_tree(NBodySim& s)
         B200_CHECK(cudaMemsetAsync(s.other, 0xff, (size_t)n * sizeof(int), st));
         build_kernel<<<grid, 256, 0, st>>>(s.keys[s.sorted_slot], s.pos[s.cur], s.mass[s.cur], n, s.childL, s.childR,
                                            s.parent, s.other, s.range, s.msum, s.d_root);
+        ++s.launches;
         B200_CHECK(cudaGetLastError());
     }
     s.timer.mark(st);
@@ -594,8 +622,10 @@ void nbody_build_tree(NBodySim& s)
                                                   s.nchild, s.d_alloc, (unsigned)s.rec_capacity, s.d_error);
         write_records_kernel<<<g1, 256, 0, st>>>(s.keys[s.sorted_slot], n, s.childL, s.childR, s.parent, s.range, s.msum,
                                                  s.first, s.nchild, s.posm, s.d_bounds, s.theta, s.d_root, s.recs);
+        s.launches += 2;
     } else {
         single_body_record_kernel<<<1, 1, 0, st>>>(s.posm, s.recs);
+        ++s.launches;
     }
     B200_CHECK(cudaGetLastError());
     s.timer.mark(st);
@@ -616,6 +646,7 @@ void nbody_traverse(NBodySim& s, int begin, int end)
         const float eps2 = (float)(s.softening * s.softening);
         traverse_kernel<<<blocks, TRAV_BLOCK, 0, st>>>(s.recs, s.posm, s.acc, tile_begin, tile_end, min(end, s.n), eps2,
                                                        (float)s.G, s.d_tile_counter, s.d_interactions, s.d_error);
+        ++s.launches;
         B200_CHECK(cudaGetLastError());
     }
     s.timer.mark(st);
@@ -630,6 +661,7 @@ void nbody_integrate(NBodySim& s, double dt)
         B200_CHECK(cudaMemsetAsync(s.d_maxabs + next, 0, sizeof(unsigned long long), st));
         integrate_kernel<<<div_up(s.n, 256), 256, 0, st>>>(s.pos[s.cur], s.vel[s.cur], s.acc, s.n, dt, s.damping,
                                                            s.d_maxabs + next);
+        ++s.launches;
         B200_CHECK(cudaGetLastError());
         s.maxabs_slot = next;
     }
@@ -638,16 +670,67 @@ void nbody_integrate(NBodySim& s, double dt)
     ++s.steps;
 }
 
-void nbody_step(NBodySim& s, double dt)
+void nbody_step_begin(NBodySim& s)
 {
     nbody_build_tree(s);
-    nbody_traverse(s, 0, s.n);
-    s.timer.mark(s.stream);   // exchange phase: empty on one GPU
+    nbody_traverse(s, s.shard_begin, s.shard_end);
+}
+
+void nbody_step_end(NBodySim& s, double dt)
+{
+    s.timer.mark(s.stream);   // exchange phase (the caller's collective); empty on one GPU
     nbody_integrate(s, dt);
     if (s.timer.enabled) {
         B200_CHECK(cudaStreamSynchronize(s.stream));
         s.timer.collect();
     }
+}
+
+void nbody_step(NBodySim& s, double dt)
+{
+    nbody_step_begin(s);
+    nbody_step_end(s, dt);
+}
+
+// ---------------------------------------------------------------------------- FP32 peak probe
+// Dependent-free FFMA chains: 8 accumulators x 4096 iterations per thread, enough CTAs to
+// fill the machine.  Gives the measured denominator of the traversal's roofline.
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, float a, float b, int iters)
+{
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+        x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+    const float r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == 12345.678f) out[0] = r;
+}
+
+double fp32_peak_tflops(int device)
+{
+    B200_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B200_CHECK(cudaGetDeviceProperties(&prop, device));
+    float* d = dev_alloc<float>(1);
+    cudaEvent_t e0, e1;
+    B200_CHECK(cudaEventCreate(&e0));
+    B200_CHECK(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        B200_CHECK(cudaEventRecord(e0, 0));
+        ffma_peak_kernel<<<blocks, 256>>>(d, 1.0000001f, 1e-7f, iters);
+        B200_CHECK(cudaEventRecord(e1, 0));
+        B200_CHECK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        B200_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * iters * 256.0 * blocks;
+        if (rep > 0 && ms > 0) best = fmax(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return best;
 }
 
 void nbody_compute_colors(NBodySim& s, double max_speed)

@@ -83,6 +83,9 @@ struct NBodySim {
 
     PhaseTimer timer;
     int64_t steps = 0;
+    int64_t launches = 0;                     // kernels launched by this handle (bench: gpu_launches)
+    cudaStream_t own_stream = nullptr;
+    int64_t acc_capacity = 0;                 // entries in acc (padded so equal shard slices fit)
     size_t bytes_allocated = 0;
 };
 
@@ -96,6 +99,11 @@ void nbody_build_tree(NBodySim& s);
 void nbody_traverse(NBodySim& s, int begin, int end);
 void nbody_integrate(NBodySim& s, double dt);
 void nbody_step(NBodySim& s, double dt);
+// split step for sharded runs: begin = tree + traversal of [shard_begin, shard_end); the caller
+// then exchanges acc slices between ranks on the same stream; end = integrate of all bodies.
+void nbody_step_begin(NBodySim& s);
+void nbody_step_end(NBodySim& s, double dt);
+double fp32_peak_tflops(int device);
 void nbody_compute_colors(NBodySim& s, double max_speed);
 void nbody_get_positions(NBodySim& s, float* out);
 void nbody_get_positions_f64(NBodySim& s, double* out);

@@ -201,6 +201,7 @@ struct Sorter {
     unsigned* tickets = nullptr;   // [MAX_PASSES]
     size_t scratch_bytes = 0;
     unsigned char* scratch = nullptr;
+    int last_launches = 0;         // kernels launched by the last sort()
 
     static constexpr int ITEMS = Tile<K>::ITEMS;
     static constexpr int TILE = BLOCK * ITEMS;
@@ -231,6 +232,7 @@ struct Sorter {
              cudaStream_t stream, int sm_count)
     {
         B200_REQUIRE(n <= n_max, "radix sort: n exceeds workspace");
+        last_launches = 0;
         if (n <= 1 && !iota) return cur;
         const int npass = (end_bit - begin_bit + 7) / 8;
         B200_REQUIRE(npass >= 1 && npass <= MAX_PASSES, "radix sort: bad bit range");
@@ -257,6 +259,7 @@ struct Sorter {
                 cur ^= 1;
             }
             B200_CHECK(cudaGetLastError());
+            last_launches = npass + 2;
         }
         return cur;
     }

@@ -115,18 +115,27 @@ class B200BarnesHutSimulation:
     def compute_colors(self, max_speed: float):
         _lib.check(self._L.b200_nbody_compute_colors(self._handle(), float(max_speed)))
 
-    def get_positions(self) -> np.ndarray:
-        out = np.empty((self.n, 3), np.float32)
+    @staticmethod
+    def _out(out, shape, dtype):
+        """Fresh array like the reference's getters, or a caller buffer (e.g. pinned host memory)."""
+        if out is None:
+            return np.empty(shape, dtype)
+        if out.shape != shape or out.dtype != dtype or not out.flags.c_contiguous:
+            raise ValueError(f"out must be a C-contiguous {dtype} array of shape {shape}")
+        return out
+
+    def get_positions(self, out=None) -> np.ndarray:
+        out = self._out(out, (self.n, 3), np.float32)
         _lib.check(self._L.b200_nbody_get_positions(self._handle(), out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
 
-    def get_velocities(self) -> np.ndarray:
-        out = np.empty((self.n, 3), np.float64)
+    def get_velocities(self, out=None) -> np.ndarray:
+        out = self._out(out, (self.n, 3), np.float64)
         _lib.check(self._L.b200_nbody_get_velocities(self._handle(), out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
 
-    def get_colors(self) -> np.ndarray:
-        out = np.empty((self.n, 3), np.float32)
+    def get_colors(self, out=None) -> np.ndarray:
+        out = self._out(out, (self.n, 3), np.float32)
         _lib.check(self._L.b200_nbody_get_colors(self._handle(), out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
 
@@ -172,6 +181,41 @@ class B200BarnesHutSimulation:
         self.damping = self.damping if damping is None else float(damping)
         self.theta = self.theta if theta is None else float(theta)
         _lib.check(self._L.b200_nbody_set_params(self._handle(), self.G, self.softening, self.damping, self.theta))
+
+    def timed_steps(self, dt: float, nsteps: int) -> float:
+        """Runs nsteps steps; returns their device time in ms (CUDA events on the stream)."""
+        ms = C.c_float(0.0)
+        _lib.check(self._L.b200_nbody_timed_steps(self._handle(), float(dt), int(nsteps), C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        v = C.c_int64(0)
+        _lib.check(self._L.b200_nbody_launch_count(self._handle(), C.byref(v)))
+        return int(v.value)
+
+    # sharded step pieces (see b200sim.nbody.sharded for the torch.distributed plumbing)
+    def set_stream(self, cuda_stream):
+        """Run all device work on the given cudaStream_t (int; 0 = legacy default stream);
+        None returns to the handle's own stream."""
+        if cuda_stream is None:
+            _lib.check(self._L.b200_nbody_set_stream(self._handle(), None, 0))
+        else:
+            _lib.check(self._L.b200_nbody_set_stream(self._handle(), C.c_void_p(int(cuda_stream) or None), 1))
+
+    def set_shard(self, begin: int, end: int):
+        _lib.check(self._L.b200_nbody_set_shard(self._handle(), int(begin), int(end)))
+
+    def step_begin(self):
+        _lib.check(self._L.b200_nbody_step_begin(self._handle()))
+
+    def step_end(self, dt: float):
+        _lib.check(self._L.b200_nbody_step_end(self._handle(), float(dt)))
+
+    def acc_buffer(self):
+        """(device pointer, capacity in 16-byte entries) of the sorted-order accelerations."""
+        p, cap = C.c_void_p(), C.c_int64(0)
+        _lib.check(self._L.b200_nbody_acc_buffer(self._handle(), C.byref(p), C.byref(cap)))
+        return int(p.value), int(cap.value)
 
     def set_profiling(self, enabled: bool):
         _lib.check(self._L.b200_nbody_set_profiling(self._handle(), int(bool(enabled))))

@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- Barnes-Hut body-updates/s (BASELINE.json metric) on 1/2/4/8 B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload KEY] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (Morton keys -> radix sort -> LBVH/octree -> theta-MAC
+traversal -> integrate) over all bodies of the workload.  Default workload: the 50 M-body
+EXTREME galaxy at theta 0.7 (BASELINE.json configs[4]; it fits one GPU, and is the config
+quoted for 1/2/4/8 GPUs => strong scaling); the 1 M-body `4k_collision_1m` line (configs[2])
+is measured in the same run at N=1 and reported under "also".  Inputs are synthetic, seeded,
+generated on the host and resident in HBM before the timed region; per-step touched data is
+far larger than the 126 MB L2 at both sizes (no L2 flush needed).
+
+Prints ONE JSON line on rank 0.  `--impl reference` times the reference's CPU path
+(the oracle port of its Numba kernels, all host cores) on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_INTERACTION = 20          # GPU-Gems-3 convention
+CPU_SAMPLE_BODIES = 1_000_000      # bounded CPU sample (full oracle step on this many bodies)
+# algorithmic HBM bytes per body per phase (DESIGN.md "Kernels"), fp64 master state
+PHASE_BYTES = {"keygen": 24 + 8, "sort": 8 + 8 * (12 + 12), "gather": 4 + 60 + 60 + 16,
+               "build": 8 + 32 + 16 + 4 + 4 + 8 + 32 + 4, "extract": 2 * (8 + 12 + 8) + 8 + 48 + 48,
+               "integrate": 16 + 48 + 48}
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _dist_env():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, local, world
+
+
+def _workload(key: str, bodies: int | None):
+    import b200sim  # noqa: F401
+    from b200sim import presets
+    t0 = time.time()
+    cfg, pos, vel, mass = presets.generate_preset(key, seed=0, num_bodies=bodies)
+    return cfg, pos, vel, mass, time.time() - t0
+
+
+# ----------------------------------------------------------------------------- CPU baseline
+def cpu_step_sample(cfg, pos, vel, mass, sample: int):
+    """One full oracle substep (tools/record.py:835-858 sequence) on the first `sample` bodies."""
+    from oracle import oracle as orc
+    n = min(sample, len(pos))
+    p, v, m = pos[:n].copy(), vel[:n].copy(), mass[:n].copy()
+    t0 = time.perf_counter()
+    orc.nbody_step(p, v, m, cfg["theta"], cfg["G"], cfg["softening"], cfg["damping"], cfg["dt"])
+    return n, time.perf_counter() - t0
+
+
+def cpu_baseline(cfg, pos, vel, mass, reps: int = 1):
+    from oracle import oracle as orc
+    best, n = None, 0
+    for _ in range(reps):
+        n, t = cpu_step_sample(cfg, pos, vel, mass, CPU_SAMPLE_BODIES)
+        best = t if best is None else min(best, t)
+    return {"value": n / best, "unit": "body-updates/s", "cores": orc.num_threads(), "kind": "port",
+            "sample": f"one full oracle substep (bounds, sequential octree build, BH forces on all cores, "
+                      f"integrate) on the first {n:,} bodies of the workload; {best:.2f} s"}
+
+
+def run_reference(args):
+    rank, _local, world = _dist_env()
+    if rank != 0:
+        return 0
+    key = args.workload or "extreme_50m_galaxy_t07"
+    from oracle import oracle as orc
+    orc.build()
+    cfg, pos, vel, mass, _ = _workload(key, min(args.bodies or 10 ** 12, CPU_SAMPLE_BODIES))
+    for _ in range(min(args.warmup, 1)):          # no JIT to warm: one touch is enough
+        cpu_step_sample(cfg, pos, vel, mass, CPU_SAMPLE_BODIES)
+    times, n = [], len(pos)
+    for _ in range(args.steps):
+        n, t = cpu_step_sample(cfg, pos, vel, mass, CPU_SAMPLE_BODIES)
+        times.append(t)
+    total = sum(times)
+    value = n * len(times) / total
+    line = {
+        "impl": "reference", "metric": "body_updates_per_sec", "value": value, "unit": "body-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": key, "bodies": cfg["num_bodies"], "theta": cfg["theta"], "G": cfg["G"],
+                   "softening": cfg["softening"], "dt": cfg["dt"], "sample_bodies": n},
+        "cpu_baseline": {"value": value, "unit": "body-updates/s", "cores": orc.num_threads(), "kind": "port",
+                         "sample": f"each step = one full oracle substep on a {n:,}-body sample of the workload "
+                                   "(the reference's Numba path cannot travel to the GPU box; its 8 M-node cap also "
+                                   "makes it invalid above ~5.4 M bodies)"},
+        "e2e": {"value": value, "unit": "body-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def _make_sim(cfg, pos, vel, mass, device, rank, world, torch):
+    from b200sim.nbody.gpu_backend import B200BarnesHutSimulation
+    from b200sim.nbody.sharded import ShardedSimulation
+    sim = B200BarnesHutSimulation(pos, vel, mass, cfg["G"], cfg["softening"], cfg["damping"], cfg["theta"],
+                                  device=device)
+    return ShardedSimulation(sim, rank, world)
+
+
+def _timed(sh, dt, steps, torch, dist, world):
+    """K steps bracketed by barrier + device synchronize; device time by CUDA events on the
+    stream the kernels run on (torch's current stream); max over ranks."""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        sh.step(dt)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, quiet=False):
+    cfg, pos, vel, mass, gen_s = _workload(key, bodies)
+    n = len(pos)
+    dt = cfg["dt"]
+    sh = _make_sim(cfg, pos, vel, mass, local, rank, world, torch)
+    sim = sh.sim
+    for _ in range(max(args.warmup, 3)):
+        sh.step(dt)
+    torch.cuda.synchronize()
+
+    # ---- headline: device-timed steps, inputs resident
+    launches0 = sim.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ms_total = _timed(sh, dt, args.steps, torch, dist, world)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sim.launch_count() - launches0
+    ms_per_step = ms_total / args.steps
+    value = n / (ms_per_step * 1e-3)
+
+    # ---- per-phase device times (CUDA events inside the library, same stream), separate pass
+    sim.reset_stats()
+    sim.set_profiling(True)
+    for _ in range(args.steps):
+        sh.step(dt)
+    torch.cuda.synchronize()
+    st = sim.get_stats()
+    sim.set_profiling(False)
+    phase = {k: v / max(st["timed_steps"], 1) for k, v in st["phase_ms"].items()}
+    inter = torch.tensor([float(st["interactions"]) / max(st["timed_steps"], 1)], device="cuda", dtype=torch.float64)
+    trav = torch.tensor([phase["traverse"]], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(inter, op=dist.ReduceOp.SUM)
+        dist.all_reduce(trav, op=dist.ReduceOp.MAX)
+    inter_step, trav_ms = float(inter.item()), float(trav.item())
+
+    out = dict(cfg=cfg, n=n, gen_s=gen_s, ms_per_step=ms_per_step, value=value, launches=launches, clocks=clocks,
+               phase=phase, inter_step=inter_step, trav_ms=trav_ms, stats=st, pos=pos, vel=vel, mass=mass)
+
+    # ---- end to end through the reference-facing API with HOST buffers
+    if with_e2e:
+        pin_pos = torch.from_numpy(pos).pin_memory()
+        pin_vel = torch.from_numpy(vel).pin_memory()
+        hp, hv = pin_pos.numpy(), pin_vel.numpy()
+        out_p = torch.empty((n, 3), dtype=torch.float32).pin_memory().numpy()
+        out_c = torch.empty((n, 3), dtype=torch.float32).pin_memory().numpy()
+        e2e_steps = max(2, min(args.steps, 5))
+        def frame():
+            sim.set_state(hp, hv)              # H2D of the step's inputs (48 B/body, pinned)
+            sh.step(dt)
+            sim.compute_colors(15.0)
+            p32 = sim.get_positions(out=out_p)  # D2H (12 B/body), as tools/record.py:828
+            c32 = sim.get_colors(out=out_c)     # D2H (12 B/body), as tools/record.py:829
+            return p32, c32
+        frame()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            frame()
+        torch.cuda.synchronize()
+        el = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        out["e2e"] = {"value": n * e2e_steps / float(el.item()), "unit": "body-updates/s",
+                      "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 24 * n, "steps": e2e_steps,
+                      "what": "set_state(pos,vel) from pinned host memory + step + compute_colors + "
+                              "get_positions + get_colors into pinned host buffers, per step, through the ctypes C-ABI"}
+    sim.close()
+    return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank, local, world = _dist_env()
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+        local = 0
+    import b200sim
+    from b200sim import _lib
+    _lib.load()   # fails loudly if the CUDA library is missing
+
+    key = args.workload or "extreme_50m_galaxy_t07"
+    m = _measure(key, args.bodies, args, rank, local, world, torch, dist)
+    cfg, n = m["cfg"], m["n"]
+
+    peaks, peak_src = _peaks()
+    fp32_peak = _lib.fp32_peak_tflops(local)
+    achieved = FLOP_PER_INTERACTION * m["inter_step"] / (m["trav_ms"] * 1e-3) / 1e12 / world   # per GPU
+    roofline = {
+        "kernel": "traverse_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
+        "peak_source": "measured in this run: FFMA-chain microbenchmark (b200_fp32_peak_tflops); "
+                       "MEASURED_PEAKS.json has no FP32 entry; nominal 148 SM x 128 x 2 x 1.965 GHz = 74.4",
+        "algorithmic_flop_per_launch": FLOP_PER_INTERACTION * m["inter_step"] / world,
+        "interactions_per_body": m["inter_step"] / n, "launch_ms": m["trav_ms"],
+        "note": "per GPU; not tensor-core work (no dense contraction); HBM phases under 'phases'",
+    }
+    phases = {}
+    for k, v in m["phase"].items():
+        e = {"ms": v}
+        if k in PHASE_BYTES and v > 0:
+            gbs = PHASE_BYTES[k] * n / (v * 1e-3) / 1e9
+            e.update(algorithmic_bytes_per_body=PHASE_BYTES[k], achieved_gbs=gbs, frac_of_hbm_peak=gbs / peaks["hbm_gbs"])
+        phases[k] = e
+
+    line = {
+        "metric": "body_updates_per_sec", "value": m["value"], "unit": "body-updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": m["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": key, "bodies": n, "theta": cfg["theta"], "G": cfg["G"], "softening": cfg["softening"],
+                   "dt": cfg["dt"], "distribution": cfg["distribution"], "seed": 0,
+                   "parallelism": f"morton-range x{world}, replicated tree, allgather(acc)",
+                   "l2": "per-step working set >> 126 MB L2 (no flush needed)",
+                   "state_dtype": "f64 positions/velocities, f32 forces"},
+        "steps_per_sec": 1e3 / m["ms_per_step"],
+        "roofline": roofline, "phases": phases, "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_peak_source": peak_src,
+        "e2e": m.get("e2e"), "gpu_launches": m["launches"], "clocks": m["clocks"],
+        "host_generate_s": m["gen_s"],
+    }
+    if rank == 0 and world == 1:
+        line["cpu_baseline"] = cpu_baseline(cfg, m["pos"], m["vel"], m["mass"])
+    del m
+    if world == 1 and key != "4k_collision_1m" and not args.no_also:
+        a = _measure("4k_collision_1m", None, args, rank, local, world, torch, dist, with_e2e=True)
+        ach = FLOP_PER_INTERACTION * a["inter_step"] / (a["trav_ms"] * 1e-3) / 1e12
+        line["also"] = {"workload": "4k_collision_1m", "bodies": a["n"], "theta": a["cfg"]["theta"],
+                        "value": a["value"], "unit": "body-updates/s", "ms_per_step": a["ms_per_step"],
+                        "phases_ms": a["phase"], "interactions_per_body": a["inter_step"] / a["n"],
+                        "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                                     "frac": ach / fp32_peak if fp32_peak else None},
+                        "e2e": a.get("e2e"),
+                        "cpu_baseline": cpu_baseline(a["cfg"], a["pos"], a["vel"], a["mass"])}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, help="preset key (b200sim.presets.PRESETS)")
+    ap.add_argument("--bodies", type=int, default=None, help="override the preset's body count")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary 1 M-body line")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

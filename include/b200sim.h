@@ -84,6 +84,68 @@ int b200_nbody_get_perm(b200_nbody* h, uint32_t* out);
 int b200_nbody_get_stats(b200_nbody* h, b200_nbody_stats* out);
 int b200_nbody_reset_stats(b200_nbody* h);
 int b200_nbody_set_profiling(b200_nbody* h, int enabled);
+/* Runs nsteps steps and returns their device time (CUDA events on the handle's stream). */
+int b200_nbody_timed_steps(b200_nbody* h, double dt, int nsteps, float* elapsed_ms);
+/* Kernels launched by this handle so far (bench.py's gpu_launches). */
+int b200_nbody_launch_count(b200_nbody* h, int64_t* out);
+
+/* ---- sharded (multi-GPU) step ------------------------------------------------------------
+ * One process per GPU, every rank holds the full replicated state and builds the full tree;
+ * a rank traverses only sorted bodies [begin, end) (begin a multiple of 32).  Between
+ * step_begin and step_end the host-side plumbing (torch.distributed / NCCL) all-gathers the
+ * accelerations buffer slices on the SAME stream (set_stream), then every rank integrates all
+ * bodies, which keeps the replicas bit-identical.  No reference counterpart. */
+/* external != 0: run all work of the handle on cuda_stream (a cudaStream_t; 0 is the legacy
+ * default stream); external == 0: back to the handle's own non-blocking stream. */
+int b200_nbody_set_stream(b200_nbody* h, void* cuda_stream, int external);
+int b200_nbody_set_shard(b200_nbody* h, int64_t begin, int64_t end);
+int b200_nbody_step_begin(b200_nbody* h);
+int b200_nbody_step_end(b200_nbody* h, double dt);
+/* Device address and capacity (in float4 entries of 16 bytes) of the sorted-order
+ * accelerations buffer {ax, ay, az, interaction count}. */
+int b200_nbody_acc_buffer(b200_nbody* h, void** device_ptr, int64_t* capacity_entries);
+
+/* Measured FP32 FFMA throughput of the device (TFLOP/s): the traversal's roofline denominator. */
+int b200_fp32_peak_tflops(int device, double* tflops);
+
+/* ---- boids ---------------------------------------------------------------------------------
+ * The reference has no backend layer for boids; the seam is Flock.update(dt)
+ * (boids/flock.py:627-678) mutating positions / velocities / colors (n,3) fp64.
+ * Parameters: config/boids.py:30-46 (same names). Grid: boids/flock.py:478-481. */
+typedef struct b200_boids_params {
+    double bounds, max_speed, max_force, wall_margin, wall_weight;
+    double perception_radius, separation_radius;
+    double separation_weight, alignment_weight, cohesion_weight, color_blend_rate;
+} b200_boids_params;
+
+#define B200_BOIDS_PHASES 5
+/* order: cells, sort, gather, table, rules(+physics) */
+typedef struct b200_boids_stats {
+    int64_t n, steps, num_cells;
+    int32_t grid_dim, key_bits;
+    double  cell_size, grid_offset;
+    int64_t neighbor_pairs;      /* accepted (i, j) neighbour pairs since the last reset */
+    int64_t bytes_allocated;
+    int64_t launches;
+    int64_t timed_steps;
+    double  phase_ms[B200_BOIDS_PHASES];
+} b200_boids_stats;
+
+int b200_boids_create(int64_t n, const double* pos, const double* vel, const double* col,
+                      const b200_boids_params* params, int device, b200_boids** out);
+int b200_boids_destroy(b200_boids* h);
+/* one Flock.update(dt): grid build + rules + physics, state stays on the device */
+int b200_boids_step(b200_boids* h, double dt);
+/* creation order; any of the three pointers may be NULL to skip that array */
+int b200_boids_get_state(b200_boids* h, double* pos, double* vel, double* col);
+int b200_boids_set_state(b200_boids* h, const double* pos, const double* vel, const double* col);
+/* cell index of every boid of the current state (assign_cells, boids/flock.py:30-44) */
+int b200_boids_get_cell_indices(b200_boids* h, int32_t* out);
+int b200_boids_get_stats(b200_boids* h, b200_boids_stats* out);
+int b200_boids_reset_stats(b200_boids* h);
+int b200_boids_set_profiling(b200_boids* h, int enabled);
+int b200_boids_timed_steps(b200_boids* h, double dt, int nsteps, float* elapsed_ms);
+int b200_boids_sync(b200_boids* h);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ from b200sim import presets
 from b200sim.nbody.gpu_backend import B200BarnesHutSimulation
 
 key = sys.argv[1] if len(sys.argv) > 1 else "4k_collision_1m"
-n = int(sys.argv[2]) if len(sys.argv) > 2 else None
+n = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2] not in ("-", "None") else None
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 t0 = time.time()
 cfg, pos, vel, mass = presets.generate_preset(key, 0, n)

@@ -1,0 +1,152 @@
+"""CPU-only checks: the C-ABI library loads and exports every declared symbol, host-side
+sharding logic (gloo, world_size 2), preset tables, drop-in module surface."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_symbol_in_header():
+    import b200sim
+    from b200sim import _lib
+    L = _lib.load()
+    header = open(os.path.join(ROOT, "include", "b200sim.h")).read()
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/b200sim.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_struct_sizes_match_header_layout():
+    from b200sim import _lib
+    import ctypes as C
+    assert C.sizeof(_lib.BoidsParams) == 11 * 8
+    assert C.sizeof(_lib.NBodyStats) == 8 * 5 + 4 + 4 + 8 + 8 + 8 * 8
+    assert C.sizeof(_lib.BoidsStats) == 8 * 3 + 4 + 4 + 8 * 2 + 8 * 4 + 8 * 5
+
+
+def test_argument_errors_raise_without_a_gpu():
+    from b200sim import _lib
+    import ctypes as C
+    L = _lib.load()
+    h = C.c_void_p()
+    st = L.b200_nbody_create(-1, None, None, None, 1.0, 1.0, 1.0, 0.5, 0, C.byref(h))
+    assert st == 2 and b"n out of range" in L.b200_last_error()
+    with pytest.raises(_lib.B200Error):
+        _lib.check(st)
+    assert L.b200_nbody_step(None, 0.1) == 2
+
+
+def test_backend_module_surface_matches_reference():
+    """Names tools/record.py:760 and nbody/simulation.py:511-525 import from nbody.gpu_backend."""
+    from b200sim.nbody import gpu_backend as gb
+    for name in ("Backend", "get_backend", "force_backend", "detect_backend", "create_gpu_simulation",
+                 "CUDASimulation", "CUDA_THRESHOLD"):
+        assert hasattr(gb, name)
+    assert [m.name for m in gb.Backend] == ["CUDA", "METAL_BH", "METAL", "CPU"]
+    assert [m.value for m in gb.Backend] == ["cuda", "metal_barnes_hut", "metal", "cpu"]
+    import inspect
+    sig = inspect.signature(gb.create_gpu_simulation)
+    assert list(sig.parameters) == ["positions", "velocities", "masses", "G", "softening", "damping", "theta", "force_gpu"]
+    assert sig.parameters["theta"].default == 0.5 and sig.parameters["force_gpu"].default is False
+    for m in ("step", "compute_colors", "get_positions", "get_velocities", "get_colors", "sync"):
+        assert callable(getattr(gb.B200BarnesHutSimulation, m))
+    gb.force_backend(gb.Backend.CPU)
+    assert gb.get_backend()[0] is gb.Backend.CPU
+    assert gb.create_gpu_simulation(np.zeros((4, 3)), np.zeros((4, 3)), np.ones(4), 0.1, 1.0, 1.0) is None
+
+
+def test_config_mirrors_reference_values():
+    from b200sim.config import nbody, boids
+    assert nbody.NBODY["G"] == 0.1 and nbody.NBODY["softening"] == 2.0 and nbody.NBODY["theta"] == 0.8
+    assert nbody.NBODY["damping"] == 1.0 and nbody.NBODY["max_speed_color"] == 15.0
+    assert boids.BOIDS["perception_radius"] == 5.0 and boids.BOIDS["separation_radius"] == 3.0
+    assert boids.BOIDS["bounds"] == 500.0 and boids.BOIDS["max_force"] == 60.0
+
+
+def test_presets_match_reference_when_present():
+    from b200sim import presets
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip("reference tree not present")
+    ref = refimport.load()
+    for key, mine in presets.PRESETS.items():
+        rkey = {"extreme_50m_galaxy_t07": "extreme_50m_galaxy", "accurate_cluster_100k": "accurate_cluster"}.get(key, key)
+        theirs = ref.get_preset_config(rkey)
+        for k in ("G", "softening", "damping", "spawn_radius", "distribution", "dt_per_frame", "substeps"):
+            if key == "accurate_cluster_100k" and k in ("dt_per_frame", "substeps"):
+                continue
+            assert mine[k] == theirs[k], (key, k)
+        if key not in ("extreme_50m_galaxy_t07", "accurate_cluster_100k"):
+            assert mine["theta"] == theirs["theta"] and mine["num_bodies"] == theirs["num_bodies"]
+
+
+def test_synthetic_generators_are_seeded_and_shaped():
+    from b200sim import presets
+    for dist in ("galaxy", "collision", "cluster", "sphere"):
+        p1, v1, m1 = presets.generate(dist, 5000, 300.0, 0.1, seed=3)
+        p2, v2, m2 = presets.generate(dist, 5000, 300.0, 0.1, seed=3)
+        assert np.array_equal(p1, p2) and np.array_equal(v1, v2)
+        assert p1.shape == (5000, 3) and p1.dtype == np.float64 and m1.shape == (5000,)
+        assert np.isfinite(p1).all() and np.isfinite(v1).all()
+    p, _, _ = presets.generate("galaxy", 20000, 500.0, 0.1, 0)
+    assert np.abs(p[:, 1]).mean() < 0.15 * np.abs(p[:, 0]).mean()       # thin disk in the XZ plane
+
+
+def test_partition_covers_all_bodies_in_whole_tiles():
+    from b200sim.nbody import sharded
+    for n in (0, 1, 31, 32, 33, 1000, 50_000_000, 1_000_003):
+        for world in (1, 2, 3, 4, 8):
+            parts = sharded.partition_equal(n, world)
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            for (b0, e0), (b1, e1) in zip(parts, parts[1:]):
+                assert e0 == b1
+            for b, e in parts:
+                assert b <= e and (b % 32 == 0 or b == e)
+            assert sharded.slice_size(n, world) * world >= n
+
+
+def _gloo_worker(rank, world, port, n, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import b200sim  # noqa: F401
+    from b200sim.nbody import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    S = sharded.slice_size(n, world)
+    b, e = sharded.partition_equal(n, world)[rank]
+    buf = torch.full((S * world, 4), -1.0)
+    # each rank "traverses" its own slice: value encodes the sorted position
+    buf[b:e, 0] = torch.arange(b, e, dtype=torch.float32)
+    buf[b:e, 1] = float(rank)
+    sharded.all_gather_slices(buf, rank, world)
+    ok = bool((buf[:n, 0] == torch.arange(n, dtype=torch.float32)).all())
+    owners = buf[:n, 1].clone()
+    expect = torch.zeros(n)
+    for r, (bb, ee) in enumerate(sharded.partition_equal(n, world)):
+        expect[bb:ee] = r
+    ok = ok and bool((owners == expect).all())
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [1000, 77])
+def test_all_gather_slices_gloo_world2(n):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + n % 7
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
