@@ -19,6 +19,7 @@ class NBodyStats(C.Structure):
         ("n", C.c_int64), ("steps", C.c_int64), ("records", C.c_int64), ("interactions", C.c_int64),
         ("bounds", C.c_double), ("error_flags", C.c_uint32), ("sm_count", C.c_int32),
         ("bytes_allocated", C.c_int64), ("timed_steps", C.c_int64), ("phase_ms", C.c_double * N_PHASES),
+        ("pair_records", C.c_int64),
     ]
 
 
@@ -74,6 +75,7 @@ SIGNATURES = {
     "b200_nbody_get_stats": (C.c_int, [_h, C.POINTER(NBodyStats)]),
     "b200_nbody_reset_stats": (C.c_int, [_h]),
     "b200_nbody_set_profiling": (C.c_int, [_h, C.c_int]),
+    "b200_nbody_set_counting": (C.c_int, [_h, C.c_int]),
     "b200_nbody_timed_steps": (C.c_int, [_h, C.c_double, C.c_int, C.POINTER(C.c_float)]),
     "b200_nbody_launch_count": (C.c_int, [_h, C.POINTER(C.c_int64)]),
     "b200_nbody_set_stream": (C.c_int, [_h, C.c_void_p, C.c_int]),

@@ -205,7 +205,10 @@ B200_API int b200_nbody_get_stats(b200_nbody* h, b200_nbody_stats* out)
         B200_CHECK(cudaMemcpy(&err, s.d_error, sizeof(err), cudaMemcpyDeviceToHost));
         B200_CHECK(cudaMemcpy(&inter, s.d_interactions, sizeof(inter), cudaMemcpyDeviceToHost));
         B200_CHECK(cudaMemcpy(&out->bounds, s.d_bounds, sizeof(double), cudaMemcpyDeviceToHost));
-        out->records = s.n > 1 ? (int64_t)alloc : s.n;
+        unsigned kids = 0;
+        B200_CHECK(cudaMemcpy(&kids, s.d_children, sizeof(kids), cudaMemcpyDeviceToHost));
+        out->records = s.n > 1 ? (int64_t)kids + 1 : s.n;   // root + every cell's children
+        out->pair_records = s.n > 1 ? (int64_t)alloc : 1;
         out->interactions = (int64_t)inter;
         out->error_flags = err;
         out->sm_count = s.sm_count;
@@ -231,6 +234,13 @@ B200_API int b200_nbody_set_profiling(b200_nbody* h, int enabled)
 {
     B200_ARG(h, "handle is null");
     h->sim.timer.enabled = enabled != 0;
+    return B200_OK;
+}
+
+B200_API int b200_nbody_set_counting(b200_nbody* h, int enabled)
+{
+    B200_ARG(h, "handle is null");
+    h->sim.count_interactions = enabled != 0;
     return B200_OK;
 }
 

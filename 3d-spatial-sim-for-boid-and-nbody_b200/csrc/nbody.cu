@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(256) count_children_kernel(const uint64_t* __r
                                                              const int* __restrict__ childL, const int* __restrict__ childR,
                                                              const int* __restrict__ parent, const int2* __restrict__ range,
                                                              int* __restrict__ first, int* __restrict__ nchild,
-                                                             unsigned* alloc, unsigned capacity, unsigned* error)
+                                                             unsigned* alloc, unsigned capacity, unsigned* error,
+                                                             unsigned* children_total)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
@@ -198,8 +199,13 @@ __global__ void __launch_bounds__(256) count_children_kernel(const uint64_t* __r
     // block-aggregated allocation of the child blocks: ONE atomic per CTA on the shared counter
     // (a per-thread atomicAdd on one address serialises in L2: 21 ms at 50 M bodies).
     __shared__ unsigned wsum[8];
+    __shared__ unsigned wkids[8];
     __shared__ unsigned s_base;
-    unsigned inc = (unsigned)cnt;
+    unsigned kids = (unsigned)cnt;
+    for (int o = 16; o > 0; o >>= 1) kids += __shfl_xor_sync(0xffffffffu, kids, o);
+    if (lane_id() == 0) wkids[threadIdx.x >> 5] = kids;
+    const unsigned npair = (unsigned)(cnt + 1) >> 1;   // children are stored two per 64-byte pair record
+    unsigned inc = npair;
     for (int o = 1; o < 32; o <<= 1) {
         const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane_id() >= (unsigned)o) inc += t;
@@ -209,7 +215,9 @@ __global__ void __launch_bounds__(256) count_children_kernel(const uint64_t* __r
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned tot = 0;
-        for (int w = 0; w < 8; ++w) { const unsigned t = wsum[w]; wsum[w] = tot; tot += t; }
+        unsigned ktot = 0;
+        for (int w = 0; w < 8; ++w) { const unsigned t = wsum[w]; wsum[w] = tot; tot += t; ktot += wkids[w]; }
+        if (ktot) atomicAdd(children_total, ktot);
         unsigned base = tot ? atomicAdd(alloc, tot) : 0u;
         if (base + tot > capacity) { atomicOr(error, (unsigned)ERR_RECORD_OVERFLOW); base = 0xffffffffu; }
         s_base = base;
@@ -218,18 +226,41 @@ __global__ void __launch_bounds__(256) count_children_kernel(const uint64_t* __r
     if (i >= n - 1) return;
     if (cnt == 0 || s_base == 0xffffffffu) { nchild[i] = 0; first[i] = -1; return; }
     nchild[i] = cnt;
-    first[i] = (int)(s_base + wsum[warp] + inc - (unsigned)cnt);
+    first[i] = (int)(s_base + wsum[warp] + inc - npair);
 }
 
-__device__ __forceinline__ void write_cell_record(float4* __restrict__ recs, int slot, const D4& S, int level, double bounds,
-                                                  double theta, int first, int nchild)
+// Pair records: children 2j and 2j+1 of a cell share one 64-byte record laid out for packed
+// fp32x2 math in the traversal (component c = child & 1):
+//   q0 = {x0, x1, y0, y1}   q1 = {z0, z1, m0, m1}   q2 = {T0, T1, first0, first1}
+//   q3 = {nchild0, nchild1, body0, body1}
+// T = max(size^2/theta^2, eps^2) for a cell (clamped to REC_T_MAX; theta = 0 => REC_T_MAX, "always
+// open"), eps^2 for a leaf.  An odd child count is padded with a massless dummy far away.
+constexpr float REC_T_MAX = 1e30f;        // above any real squared distance, below the sentinels'
+constexpr float REC_LANE_SENTINEL = 1e18f;   // x of a lane that is not in an entry's mask
+constexpr float REC_DUMMY_X = 3e18f;      // x of a padding child
+
+__device__ __forceinline__ void put_child(float4* __restrict__ recs, int64_t pair, int comp, float x, float y, float z,
+                                          float m, float T, int first, int nchild, int body)
+{
+    float* q = reinterpret_cast<float*>(recs + 4 * pair) + comp;
+    q[0] = x; q[2] = y; q[4] = z; q[6] = m; q[8] = T;
+    q[10] = __int_as_float(first); q[12] = __int_as_float(nchild); q[14] = __int_as_float(body);
+}
+
+__device__ __forceinline__ void put_dummy(float4* __restrict__ recs, int64_t pair)
+{
+    put_child(recs, pair, 1, REC_DUMMY_X, 0.f, 0.f, 0.f, 0.f, 0, 0, -1);
+}
+
+__device__ __forceinline__ void put_cell(float4* __restrict__ recs, int64_t pair, int comp, const D4& S, int level,
+                                         double bounds, double theta, float eps2, int first, int nchild)
 {
     const double inv = S.w > 0.0 ? 1.0 / S.w : 0.0;
     // cell size = 2*bounds / 2^level; MAC  size/d < theta  <=>  d^2 > size^2/theta^2
     const double size = ldexp(2.0 * bounds, -level);
-    const float thr = theta > 0.0 ? (float)((size * size) / (theta * theta)) : __int_as_float(0x7f800000);
-    recs[2 * (int64_t)slot] = make_float4((float)(S.x * inv), (float)(S.y * inv), (float)(S.z * inv), (float)S.w);
-    recs[2 * (int64_t)slot + 1] = make_float4(thr, __int_as_float(first), __int_as_float(nchild), __int_as_float(-1));
+    float T = REC_T_MAX;
+    if (theta > 0.0) T = fminf(fmaxf((float)fmin((size * size) / (theta * theta), 1e31), eps2), REC_T_MAX);
+    put_child(recs, pair, comp, (float)(S.x * inv), (float)(S.y * inv), (float)(S.z * inv), (float)S.w, T, first, nchild, -1);
 }
 
 __global__ void __launch_bounds__(256) write_records_kernel(const uint64_t* __restrict__ keys, int n,
@@ -237,7 +268,7 @@ __global__ void __launch_bounds__(256) write_records_kernel(const uint64_t* __re
                                                             const int* __restrict__ parent, const int2* __restrict__ range,
                                                             const D4* __restrict__ msum, const int* __restrict__ first,
                                                             const int* __restrict__ nchild, const float4* __restrict__ posm,
-                                                            const double* __restrict__ bounds_p, double theta,
+                                                            const double* __restrict__ bounds_p, double theta, float eps2,
                                                             const int* __restrict__ root, float4* __restrict__ recs)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -246,36 +277,61 @@ __global__ void __launch_bounds__(256) write_records_kernel(const uint64_t* __re
     if (nc == 0) return;
     const double bounds = *bounds_p;
     const int Li = level_of(cpl(keys, i, n));
-    if (i == *root) write_cell_record(recs, 0, msum[i], Li, bounds, theta, first[i], nc);
-    int slot = first[i];
-    for_each_octree_child(keys, n, childL, childR, range, i, Li, [&](int c) {
-        if (c < 0) {
-            const int k = ~c;
-            recs[2 * (int64_t)slot] = posm[k];
-            recs[2 * (int64_t)slot + 1] = make_float4(-1.0f, __int_as_float(0), __int_as_float(0), __int_as_float(k));
+    if (i == *root) {   // pair 0 = {root cell, dummy}
+        put_cell(recs, 0, 0, msum[i], Li, bounds, theta, eps2, first[i], nc);
+        put_dummy(recs, 0);
+    }
+    const int64_t base = first[i];
+    int c = 0;
+    for_each_octree_child(keys, n, childL, childR, range, i, Li, [&](int ch) {
+        const int64_t pair = base + (c >> 1);
+        if (ch < 0) {
+            const int k = ~ch;
+            const float4 b = posm[k];
+            put_child(recs, pair, c & 1, b.x, b.y, b.z, b.w, eps2, 0, 0, k);
         } else {
-            write_cell_record(recs, slot, msum[c], level_of(cpl(keys, c, n)), bounds, theta, first[c], nchild[c]);
+            put_cell(recs, pair, c & 1, msum[ch], level_of(cpl(keys, ch, n)), bounds, theta, eps2, first[ch], nchild[ch]);
         }
-        ++slot;
+        ++c;
     });
+    if (nc & 1) put_dummy(recs, base + (nc >> 1));
 }
 
 // single body: the root record is that leaf
-__global__ void single_body_record_kernel(const float4* __restrict__ posm, float4* __restrict__ recs)
+__global__ void single_body_record_kernel(const float4* __restrict__ posm, float eps2, float4* __restrict__ recs)
 {
-    recs[0] = posm[0];
-    recs[1] = make_float4(-1.0f, __int_as_float(0), __int_as_float(0), __int_as_float(0));
+    const float4 b = posm[0];
+    put_child(recs, 0, 0, b.x, b.y, b.z, b.w, eps2, 0, 0, 0);
+    put_dummy(recs, 0);
 }
 
 // ============================================================================ traversal
 // One warp owns 32 consecutive sorted bodies (one per lane).  The warp walks the octree with
-// a shared stack in shared memory whose entries are (child block, lane mask): only cells that
-// some lane must OPEN are pushed, with the mask of exactly those lanes, so every lane makes
-// the reference's own per-body MAC decision (nbody/simulation.py:256-258) -- no group MAC.
-// Opening a cell loads its contiguous child records with one coalesced 16 B/lane load into a
-// per-warp staging buffer; each child is then evaluated by all lanes from a shared-memory
-// broadcast:  d2 = |com - p|^2 + eps^2;  accept iff d2 > size^2/theta^2 (leaf: always);
-// accepted and d2 > eps^2 (:260, also excludes the body itself): a += m (com - p) d2^-3/2.
+// a shared stack in shared memory whose entries are (child block, child count, lane mask):
+// only cells that some lane must OPEN are pushed, with the mask of exactly those lanes, so
+// every lane makes the reference's own per-body MAC decision (nbody/simulation.py:256-258) --
+// no group MAC.  Opening a cell loads its contiguous pair records with one coalesced
+// 16 B/lane load into a per-warp staging buffer; the children are then evaluated TWO per
+// iteration from shared-memory broadcasts with Blackwell's packed fp32x2 instructions
+// (FADD2/FMUL2/FFMA2, sm_100+):
+//   d2 = |com - p|^2 + eps^2;   open iff d2 <= T;   otherwise a += m (com - p) d2^-3/2
+// with T = max(size^2/theta^2, eps^2) (leaf: eps^2).  This is the reference's "accept iff
+// size/d < theta, add iff d^2 > eps^2" (:258-267): for size^2/theta^2 >= eps^2 the tests
+// coincide; otherwise the cell is always accepted and only d2 == eps^2 (zero distance: the
+// body itself) is excluded -- it "opens" nothing because leaves have no children.
+// Lanes outside an entry's mask take x = 1e18: d2 ~ 1e36 > T, so they never open, and their
+// "contribution" m * d2^-3/2 underflows to exactly 0; no per-child mask logic is needed.
+// The kernel is instruction-issue bound (ncu: ~90 % issue-slot utilisation), so the inner loop
+// is written for instruction count.  acc.w carries the lane's child evaluations (a cost proxy
+// for load balancing); with COUNT it is the exact interaction count = evaluations - opens.
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+template <bool COUNT>
 __global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const float4* __restrict__ recs, const float4* __restrict__ posm,
                                                               float4* __restrict__ acc, int tile_begin, int tile_end, int n,
                                                               float eps2, float G, unsigned* tile_counter,
@@ -288,6 +344,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const float4* __re
     uint4* stack = s_stack[warp];
     float4* stage = s_stage[warp];
     unsigned long long wcount = 0;
+    const float2 eps22 = make_float2(eps2, eps2);
 
     for (;;) {
         unsigned t = 0;
@@ -298,8 +355,9 @@ __global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const float4* __re
         const int k = tile * 32 + (int)lane;
         const bool valid = k < n;
         const float4 p = valid ? posm[k] : make_float4(0.f, 0.f, 0.f, 0.f);
-        float ax = 0.f, ay = 0.f, az = 0.f;
-        int cnt = 0;
+        const float2 npy = make_float2(-p.y, -p.y), npz = make_float2(-p.z, -p.z);
+        float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;   // (even, odd) children accumulate separately
+        int evals = 0, opens = 0;
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         int sp = 0;
         if (lane == 0) stack[0] = make_uint4(0u, 1u, vmask, 0u);
@@ -307,33 +365,56 @@ __global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const float4* __re
         __syncwarp();
         while (sp > 0) {
             const uint4 e = stack[--sp];
-            const int first = (int)e.x, nch = (int)e.y;
+            const int first = (int)e.x;
+            int nch = (int)e.y;
+            __syncwarp();
+            if (nch > TRAV_STAGE) {   // rare (bucket of coincident bodies): leave the remainder on the stack
+                if (lane == 0) stack[sp] = make_uint4(e.x + TRAV_STAGE / 2, e.y - TRAV_STAGE, e.z, 0u);
+                ++sp;
+                nch = TRAV_STAGE;
+            }
+            const int npairs = (nch + 1) >> 1;
+            if ((int)lane < 4 * npairs) stage[lane] = __ldg(&recs[4 * (int64_t)first + lane]);
             const bool in = (e.z >> lane) & 1u;
-            for (int base = 0; base < nch; base += TRAV_STAGE) {
-                const int cn = min(TRAV_STAGE, nch - base);
-                __syncwarp();
-                if ((int)lane < 2 * cn) stage[lane] = __ldg(&recs[2 * (int64_t)(first + base) + lane]);
-                __syncwarp();
-                for (int c = 0; c < cn; ++c) {
-                    const float4 A = stage[2 * c];
-                    const float4 B = stage[2 * c + 1];
-                    const float dx = A.x - p.x, dy = A.y - p.y, dz = A.z - p.z;
-                    const float d2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, eps2)));
-                    const bool accept = d2 > B.x;
-                    const unsigned om = __ballot_sync(0xffffffffu, in && !accept);
-                    if (in && accept && d2 > eps2) {
-                        const float rinv = rsqrtf(d2);
-                        const float f = A.w * rinv * rinv * rinv;
-                        ax = fmaf(dx, f, ax);
-                        ay = fmaf(dy, f, ay);
-                        az = fmaf(dz, f, az);
-                        ++cnt;
-                    }
-                    if (om) {
-                        if (sp >= TRAV_STACK) {   // cannot happen for a 21-level tree; never drop silently
-                            if (lane == 0) atomicOr(error, (unsigned)ERR_STACK_OVERFLOW);
-                        } else {
-                            if (lane == 0) stack[sp] = make_uint4(__float_as_uint(B.y), __float_as_uint(B.z), om, 0u);
+            const float qx = in ? p.x : REC_LANE_SENTINEL;
+            const float2 nqx = make_float2(-qx, -qx);
+            if (in) evals += nch;
+            __syncwarp();
+            for (int j = 0; j < npairs; ++j) {
+                const float4 XY = stage[4 * j];
+                const float4 ZM = stage[4 * j + 1];
+                const float2 T = *reinterpret_cast<const float2*>(&stage[4 * j + 2]);
+                const float2 dx = __fadd2_rn(make_float2(XY.x, XY.y), nqx);
+                const float2 dy = __fadd2_rn(make_float2(XY.z, XY.w), npy);
+                const float2 dz = __fadd2_rn(make_float2(ZM.x, ZM.y), npz);
+                const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, eps22)));
+                const bool o0 = d2.x <= T.x, o1 = d2.y <= T.y;
+                const unsigned om0 = __ballot_sync(0xffffffffu, o0);
+                const unsigned om1 = __ballot_sync(0xffffffffu, o1);
+                float2 r;
+                r.x = o0 ? 0.f : rsqrt_approx(d2.x);
+                r.y = o1 ? 0.f : rsqrt_approx(d2.y);
+                if (COUNT) {
+                    if (o0) ++opens;
+                    if (o1) ++opens;
+                }
+                const float2 f = __fmul2_rn(make_float2(ZM.z, ZM.w), __fmul2_rn(__fmul2_rn(r, r), r));
+                ax = __ffma2_rn(dx, f, ax);
+                ay = __ffma2_rn(dy, f, ay);
+                az = __ffma2_rn(dz, f, az);
+                if (om0 | om1) {
+                    const float4 M2 = stage[4 * j + 2];
+                    const float4 M3 = stage[4 * j + 3];
+                    const unsigned nc0 = __float_as_uint(M3.x), nc1 = __float_as_uint(M3.y);
+                    if (sp >= TRAV_STACK - 2) {   // cannot happen for a 21-level tree; never drop silently
+                        if (lane == 0) atomicOr(error, (unsigned)ERR_STACK_OVERFLOW);
+                    } else {
+                        if (om0 && nc0) {
+                            if (lane == 0) stack[sp] = make_uint4(__float_as_uint(M2.z), nc0, om0, 0u);
+                            ++sp;
+                        }
+                        if (om1 && nc1) {
+                            if (lane == 0) stack[sp] = make_uint4(__float_as_uint(M2.w), nc1, om1, 0u);
                             ++sp;
                         }
                     }
@@ -341,8 +422,9 @@ __global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const float4* __re
             }
             __syncwarp();
         }
-        if (valid) acc[k] = make_float4(G * ax, G * ay, G * az, __int_as_float(cnt));
-        unsigned c32 = (unsigned)cnt;
+        const int cnt = evals - opens;
+        if (valid) acc[k] = make_float4(G * (ax.x + ax.y), G * (ay.x + ay.y), G * (az.x + az.y), __int_as_float(cnt));
+        unsigned c32 = valid ? (unsigned)cnt : 0u;
         for (int o = 16; o > 0; o >>= 1) c32 += __shfl_xor_sync(0xffffffffu, c32, o);
         wcount += c32;
     }
@@ -492,8 +574,9 @@ void nbody_alloc(NBodySim& s, int n)
     s.msum = alloc_counted<D4>(s, N);
     s.first = alloc_counted<int>(s, N);
     s.nchild = alloc_counted<int>(s, N);
-    s.rec_capacity = 2 * (int64_t)N + 2;   // root + N leaves + <= N-1 cells
-    s.recs = alloc_counted<float4>(s, 2 * (size_t)s.rec_capacity);
+    // pair records: <= (children + cells) / 2 <= 1.5 N pairs, + the root pair
+    s.rec_capacity = (3 * (int64_t)N) / 2 + 16;
+    s.recs = alloc_counted<float4>(s, 4 * (size_t)s.rec_capacity);
     s.colors = alloc_counted<float>(s, 3 * N);
     s.stage = alloc_counted<double>(s, 3 * N);
     s.d_maxabs = alloc_counted<unsigned long long>(s, 2);
@@ -501,6 +584,8 @@ void nbody_alloc(NBodySim& s, int n)
     s.d_root = alloc_counted<int>(s, 1);
     s.d_alloc = alloc_counted<unsigned>(s, 1);
     s.d_tile_counter = alloc_counted<unsigned>(s, 1);
+    s.d_children = alloc_counted<unsigned>(s, 1);
+    B200_CHECK(cudaMemset(s.d_children, 0, sizeof(unsigned)));
     s.d_interactions = alloc_counted<unsigned long long>(s, 1);
     s.d_error = alloc_counted<unsigned>(s, 1);
     B200_CHECK(cudaMemset(s.d_error, 0, sizeof(unsigned)));
@@ -523,6 +608,7 @@ void nbody_free(NBodySim& s)
     cudaFree(s.posm); cudaFree(s.acc); cudaFree(s.childL); cudaFree(s.childR); cudaFree(s.parent);
     cudaFree(s.other); cudaFree(s.range); cudaFree(s.msum); cudaFree(s.first); cudaFree(s.nchild);
     cudaFree(s.recs); cudaFree(s.colors); cudaFree(s.stage); cudaFree(s.d_maxabs); cudaFree(s.d_bounds);
+    cudaFree(s.d_children);
     cudaFree(s.d_root); cudaFree(s.d_alloc); cudaFree(s.d_tile_counter); cudaFree(s.d_interactions);
     cudaFree(s.d_error);
     s.timer.destroy();
@@ -614,17 +700,18 @@ void nbody_build_tree(NBodySim& s)
     }
     s.timer.mark(st);
     // ---- octree records
+    const float eps2f = (float)(s.softening * s.softening);
     if (n > 1) {
-        const unsigned one = 1u;   // record 0 is the root
-        B200_CHECK(cudaMemcpyAsync(s.d_alloc, &one, sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        B200_CHECK(cudaMemcpyAsync(s.d_alloc, &s.h_one, sizeof(unsigned), cudaMemcpyHostToDevice, st));   // pair 0 is the root's
+        B200_CHECK(cudaMemsetAsync(s.d_children, 0, sizeof(unsigned), st));
         const int g1 = div_up(n - 1, 256);
         count_children_kernel<<<g1, 256, 0, st>>>(s.keys[s.sorted_slot], n, s.childL, s.childR, s.parent, s.range, s.first,
-                                                  s.nchild, s.d_alloc, (unsigned)s.rec_capacity, s.d_error);
+                                                  s.nchild, s.d_alloc, (unsigned)s.rec_capacity, s.d_error, s.d_children);
         write_records_kernel<<<g1, 256, 0, st>>>(s.keys[s.sorted_slot], n, s.childL, s.childR, s.parent, s.range, s.msum,
-                                                 s.first, s.nchild, s.posm, s.d_bounds, s.theta, s.d_root, s.recs);
+                                                 s.first, s.nchild, s.posm, s.d_bounds, s.theta, eps2f, s.d_root, s.recs);
         s.launches += 2;
     } else {
-        single_body_record_kernel<<<1, 1, 0, st>>>(s.posm, s.recs);
+        single_body_record_kernel<<<1, 1, 0, st>>>(s.posm, eps2f, s.recs);
         ++s.launches;
     }
     B200_CHECK(cudaGetLastError());
@@ -644,8 +731,12 @@ void nbody_traverse(NBodySim& s, int begin, int end)
         const int max_blocks = s.sm_count * 6;
         const int blocks = min(div_up(tiles, TRAV_WARPS), max_blocks);
         const float eps2 = (float)(s.softening * s.softening);
-        traverse_kernel<<<blocks, TRAV_BLOCK, 0, st>>>(s.recs, s.posm, s.acc, tile_begin, tile_end, min(end, s.n), eps2,
-                                                       (float)s.G, s.d_tile_counter, s.d_interactions, s.d_error);
+        if (s.count_interactions)
+            traverse_kernel<true><<<blocks, TRAV_BLOCK, 0, st>>>(s.recs, s.posm, s.acc, tile_begin, tile_end, min(end, s.n),
+                                                                 eps2, (float)s.G, s.d_tile_counter, s.d_interactions, s.d_error);
+        else
+            traverse_kernel<false><<<blocks, TRAV_BLOCK, 0, st>>>(s.recs, s.posm, s.acc, tile_begin, tile_end, min(end, s.n),
+                                                                  eps2, (float)s.G, s.d_tile_counter, s.d_interactions, s.d_error);
         ++s.launches;
         B200_CHECK(cudaGetLastError());
     }
@@ -784,11 +875,13 @@ void nbody_get_accelerations(NBodySim& s, float* out)
 {
     B200_CHECK(cudaSetDevice(s.device));
     if (s.n == 0) return;
-    const bool timing = s.timer.enabled;
+    const bool timing = s.timer.enabled, counting = s.count_interactions;
     s.timer.enabled = false;
+    s.count_interactions = true;
     if (!s.tree_valid) nbody_build_tree(s);
     nbody_traverse(s, 0, s.n);
     s.timer.enabled = timing;
+    s.count_interactions = counting;
     unpermute_acc_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.acc, s.id[s.cur], (float*)s.stage, s.n);
     B200_CHECK(cudaGetLastError());
     B200_CHECK(cudaMemcpyAsync(out, s.stage, 3 * (size_t)s.n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));

@@ -12,11 +12,11 @@
 //   posm       (N) float4 {x,y,z,m} of the sorted bodies (traversal targets / leaf records)
 //   binary radix tree over the sorted keys (N-1 internal nodes): childL/childR/parent,
 //                range, msum = (sum m x, sum m y, sum m z, sum m) in f64
-//   recs       octree records, 32 B each = 2 x float4:
-//                A = {com.x, com.y, com.z, mass}
-//                B = {open_threshold = size^2/theta^2 (leaf: -1), first_child, nchild, body}
-//              children of a cell are CONTIGUOUS records, so opening a cell is one
-//              coalesced 16-byte-per-lane load.
+//   recs       octree "pair records", 64 B each = 4 x float4, holding children 2j and 2j+1 of
+//              a cell side by side for packed fp32x2 math:
+//                {x0,x1,y0,y1} {z0,z1,m0,m1} {T0,T1,first0,first1} {nchild0,nchild1,body0,body1}
+//              T = max(size^2/theta^2, eps^2) (leaf: eps^2); the children of a cell are
+//              CONTIGUOUS pairs, so opening a cell is one coalesced 16-byte-per-lane load.
 //   acc        (N) float4 {ax, ay, az, interaction count} in sorted order
 #pragma once
 #include "common.cuh"
@@ -68,7 +68,9 @@ struct NBodySim {
     int maxabs_slot = 0;
     double* d_bounds = nullptr;
     int* d_root = nullptr;
-    unsigned* d_alloc = nullptr;              // record allocator
+    unsigned* d_alloc = nullptr;              // pair-record allocator
+    unsigned* d_children = nullptr;           // octree children (cells + leaves) of the last tree
+    unsigned h_one = 1u;
     unsigned* d_tile_counter = nullptr;
     unsigned long long* d_interactions = nullptr;
     unsigned* d_error = nullptr;
@@ -76,6 +78,7 @@ struct NBodySim {
     float* colors = nullptr;                  // (N,3) f32, creation order
     void* stage = nullptr;                    // (N,3) f64-sized staging for getters
     bool tree_valid = false;                  // keys/perm/tree describe the current positions
+    bool count_interactions = false;          // exact per-body interaction counts in the traversal (slower)
 
     // multi-GPU: this rank traverses sorted bodies [shard_begin, shard_end) (multiples of 32)
     int rank = 0, world = 1;

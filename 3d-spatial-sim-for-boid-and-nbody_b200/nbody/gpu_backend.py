@@ -220,6 +220,10 @@ class B200BarnesHutSimulation:
     def set_profiling(self, enabled: bool):
         _lib.check(self._L.b200_nbody_set_profiling(self._handle(), int(bool(enabled))))
 
+    def set_counting(self, enabled: bool):
+        """Exact interaction counting inside step() (get_stats()['interactions']); off by default."""
+        _lib.check(self._L.b200_nbody_set_counting(self._handle(), int(bool(enabled))))
+
     def reset_stats(self):
         _lib.check(self._L.b200_nbody_reset_stats(self._handle()))
 

@@ -219,9 +219,19 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
         sh.step(dt)
     torch.cuda.synchronize()
     st = sim.get_stats()
-    sim.set_profiling(False)
     phase = {k: v / max(st["timed_steps"], 1) for k, v in st["phase_ms"].items()}
-    inter = torch.tensor([float(st["interactions"]) / max(st["timed_steps"], 1)], device="cuda", dtype=torch.float64)
+    # interactions per step: a short counting pass (exact device-side counters cost a few
+    # instructions per child, so the timed passes above run without them)
+    sim.reset_stats()
+    sim.set_counting(True)
+    count_steps = 2
+    for _ in range(count_steps):
+        sh.step(dt)
+    torch.cuda.synchronize()
+    cst = sim.get_stats()
+    sim.set_counting(False)
+    sim.set_profiling(False)
+    inter = torch.tensor([float(cst["interactions"]) / count_steps], device="cuda", dtype=torch.float64)
     trav = torch.tensor([phase["traverse"]], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(inter, op=dist.ReduceOp.SUM)

@@ -45,6 +45,7 @@ typedef struct b200_nbody_stats {
     int64_t bytes_allocated;   /* device bytes owned by the handle */
     int64_t timed_steps;       /* steps accumulated in phase_ms */
     double  phase_ms[B200_NBODY_PHASES];
+    int64_t pair_records;      /* 64-byte pair records allocated for the last tree */
 } b200_nbody_stats;
 
 const char* b200_last_error(void);
@@ -84,6 +85,9 @@ int b200_nbody_get_perm(b200_nbody* h, uint32_t* out);
 int b200_nbody_get_stats(b200_nbody* h, b200_nbody_stats* out);
 int b200_nbody_reset_stats(b200_nbody* h);
 int b200_nbody_set_profiling(b200_nbody* h, int enabled);
+/* Exact device-side interaction counting in step() (stats.interactions); off by default because
+ * it costs a few instructions in the traversal's inner loop.  compute_accelerations always counts. */
+int b200_nbody_set_counting(b200_nbody* h, int enabled);
 /* Runs nsteps steps and returns their device time (CUDA events on the handle's stream). */
 int b200_nbody_timed_steps(b200_nbody* h, double dt, int nsteps, float* elapsed_ms);
 /* Kernels launched by this handle so far (bench.py's gpu_launches). */

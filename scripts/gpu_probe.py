@@ -21,6 +21,7 @@ for _ in range(3):
 sim.sync()
 sim.reset_stats()
 sim.set_profiling(True)
+sim.set_counting('--nocount' not in sys.argv)
 t0 = time.time()
 for _ in range(steps):
     sim.step(cfg["dt"])
