@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const float4* __re
         for (int o = 16; o > 0; o >>= 1) c32 += __shfl_xor_sync(0xffffffffu, c32, o);
         wcount += c32;
     }
-    if (lane == 0 && wcount) atomicAdd(interactions, wcount);
+    if (COUNT && lane == 0 && wcount) atomicAdd(interactions, wcount);
 }
 
 // ============================================================================ integrate

@@ -150,3 +150,24 @@ def test_all_gather_slices_gloo_world2(n):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def test_dropin_injects_backend_into_reference_imports():
+    """With the reference checkout present: `from nbody.gpu_backend import ...` as written at
+    tools/record.py:760 must resolve to the B200 module, and the recorder module must import."""
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip("reference tree not present")
+    code = (
+        "import sys; sys.path.insert(0, %r); import b200sim; from b200sim import dropin;"
+        "ours = dropin.install(%r);"
+        "from nbody.gpu_backend import get_backend, Backend, create_gpu_simulation;"
+        "import b200sim.nbody.gpu_backend as g; assert create_gpu_simulation is g.create_gpu_simulation;"
+        "import tools.record as rec; import numpy as np;"
+        "p = np.random.rand(10, 3).astype(np.float32); c = np.random.rand(10, 3).astype(np.float32);"
+        "blob = rec.compress_frame(p, c); q, d = rec.decompress_frame(blob);"
+        "assert np.array_equal(p, q) and np.array_equal(c, d); print('ok')"
+    ) % (ROOT, refimport.REFERENCE_ROOT)
+    import subprocess
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
