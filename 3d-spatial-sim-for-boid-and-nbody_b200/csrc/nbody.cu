@@ -112,7 +112,7 @@ __device__ __forceinline__ D4 ldcg_d4(const D4* p)
 __global__ void __launch_bounds__(256) build_kernel(const uint64_t* __restrict__ keys, const double* __restrict__ pos,
                                                     const double* __restrict__ mass, int n,
                                                     int* childL, int* childR, int* parent, int* other, int2* range,
-                                                    D4* msum, int* root)
+                                                    D4* msum, signed char* lvl, int* root)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(256) build_kernel(const uint64_t* __restrict__
             if (node >= 0) parent[node] = -1;
             break;
         }
-        const bool right = cpl(keys, r, n) > cpl(keys, l - 1, n);
+        const int cr = cpl(keys, r, n), cl = cpl(keys, l - 1, n);
+        const bool right = cr > cl;
         const int p = right ? r : l - 1;
         if (right) childL[p] = node; else childR[p] = node;
         if (node >= 0) parent[node] = p;
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(256) build_kernel(const uint64_t* __restrict__
         if (right) r = o; else l = o;
         msum[p] = S;
         range[p] = make_int2(l, r);
+        lvl[p] = (signed char)level_of(right ? cr : cl);   // the node's own prefix metric is the larger boundary one
         node = p;
     }
 }
@@ -156,54 +158,66 @@ __global__ void __launch_bounds__(256) build_kernel(const uint64_t* __restrict__
 // nodes with the parent's level are sub-octant groupings and are flattened away.  This is the
 // reference's octree with single-child chains collapsed to their deepest cell, whose size is
 // the one that decides the reference's MAC (all chain cells share mass and COM).
-template <typename F>
-__device__ __forceinline__ void for_each_octree_child(const uint64_t* __restrict__ keys, int n, const int* __restrict__ childL,
-                                                      const int* __restrict__ childR, const int2* __restrict__ range,
-                                                      int i, int Li, F&& emit)
-{
-    if (Li >= MORTON_LEVELS) {   // every body below shares one finest-level cell: bucket of leaves
-        const int2 rg = range[i];
-        for (int k = rg.x; k <= rg.y; ++k) emit(~k);
-        return;
-    }
-    int stack[8];
-    int sp = 0;
-    stack[sp++] = childR[i];
-    stack[sp++] = childL[i];
-    while (sp > 0) {
-        const int c = stack[--sp];
-        if (c >= 0 && level_of(cpl(keys, c, n)) == Li) {
-            stack[sp++] = childR[c];
-            stack[sp++] = childL[c];
-        } else {
-            emit(c);   // in key order == octant order
-        }
-    }
-}
+// Pass 1 walks the <= 7 same-level binary descendants of every head once, stores the <= 8
+// octree children it finds (kids[8 i .. 8 i + 7], in key = octant order) and allocates the
+// cell's pair block; pass 2 reads the list back and writes whole 64-byte pair records.
+// Cells at the finest level (bodies sharing all 63 key bits) are buckets: their children are the
+// leaves of their range, any number of them, and are written by a plain loop.
+constexpr int KIDS = 8;
 
-__global__ void __launch_bounds__(256) count_children_kernel(const uint64_t* __restrict__ keys, int n,
-                                                             const int* __restrict__ childL, const int* __restrict__ childR,
+__global__ void __launch_bounds__(256) count_children_kernel(int n, const int* __restrict__ childL, const int* __restrict__ childR,
                                                              const int* __restrict__ parent, const int2* __restrict__ range,
-                                                             int* __restrict__ first, int* __restrict__ nchild,
+                                                             const signed char* __restrict__ lvl, int* __restrict__ first,
+                                                             int* __restrict__ nchild, int4* __restrict__ kids,
                                                              unsigned* alloc, unsigned capacity, unsigned* error,
                                                              unsigned* children_total)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
     if (i < n - 1) {
-        const int Li = level_of(cpl(keys, i, n));
+        const int Li = lvl[i];
         const int par = parent[i];
-        const bool head = par < 0 || level_of(cpl(keys, par, n)) != Li;
-        if (head) for_each_octree_child(keys, n, childL, childR, range, i, Li, [&](int) { ++cnt; });
+        const bool head = par < 0 || lvl[par] != Li;
+        if (head) {
+            if (Li >= MORTON_LEVELS) {
+                const int2 rg = range[i];
+                cnt = rg.y - rg.x + 1;
+            } else {
+                int kid[KIDS];
+#pragma unroll
+                for (int q = 0; q < KIDS; ++q) kid[q] = 0;
+                int stack[4];
+                int sp = 0;
+                int c = childL[i];
+                int pending = childR[i];
+                // in-order walk without recursion: same-level subtrees are at most 3 deep
+                for (;;) {
+                    if (c >= 0 && lvl[c] == Li) {
+                        stack[sp++] = childR[c];
+                        c = childL[c];
+                        continue;
+                    }
+#pragma unroll
+                    for (int q = 0; q < KIDS; ++q)
+                        if (q == cnt) kid[q] = c;
+                    ++cnt;
+                    if (sp > 0) c = stack[--sp];
+                    else if (pending != 0x7fffffff) { c = pending; pending = 0x7fffffff; }
+                    else break;
+                }
+                kids[2 * (int64_t)i] = make_int4(kid[0], kid[1], kid[2], kid[3]);
+                kids[2 * (int64_t)i + 1] = make_int4(kid[4], kid[5], kid[6], kid[7]);
+            }
+        }
     }
-    // block-aggregated allocation of the child blocks: ONE atomic per CTA on the shared counter
+    // block-aggregated allocation of the pair blocks: ONE atomic per CTA on the shared counter
     // (a per-thread atomicAdd on one address serialises in L2: 21 ms at 50 M bodies).
     __shared__ unsigned wsum[8];
     __shared__ unsigned wkids[8];
     __shared__ unsigned s_base;
-    unsigned kids = (unsigned)cnt;
-    for (int o = 16; o > 0; o >>= 1) kids += __shfl_xor_sync(0xffffffffu, kids, o);
-    if (lane_id() == 0) wkids[threadIdx.x >> 5] = kids;
+    unsigned nk = (unsigned)cnt;
+    for (int o = 16; o > 0; o >>= 1) nk += __shfl_xor_sync(0xffffffffu, nk, o);
+    if (lane_id() == 0) wkids[threadIdx.x >> 5] = nk;
     const unsigned npair = (unsigned)(cnt + 1) >> 1;   // children are stored two per 64-byte pair record
     unsigned inc = npair;
     for (int o = 1; o < 32; o <<= 1) {
@@ -239,70 +253,97 @@ constexpr float REC_T_MAX = 1e30f;        // above any real squared distance, be
 constexpr float REC_LANE_SENTINEL = 1e18f;   // x of a lane that is not in an entry's mask
 constexpr float REC_DUMMY_X = 3e18f;      // x of a padding child
 
-__device__ __forceinline__ void put_child(float4* __restrict__ recs, int64_t pair, int comp, float x, float y, float z,
-                                          float m, float T, int first, int nchild, int body)
+struct ChildRec { float x, y, z, m, T; int first, nchild, body; };
+
+__device__ __forceinline__ ChildRec dummy_child()
 {
-    float* q = reinterpret_cast<float*>(recs + 4 * pair) + comp;
-    q[0] = x; q[2] = y; q[4] = z; q[6] = m; q[8] = T;
-    q[10] = __int_as_float(first); q[12] = __int_as_float(nchild); q[14] = __int_as_float(body);
+    return ChildRec{REC_DUMMY_X, 0.f, 0.f, 0.f, 0.f, 0, 0, -1};
 }
 
-__device__ __forceinline__ void put_dummy(float4* __restrict__ recs, int64_t pair)
+__device__ __forceinline__ float cell_threshold(int level, double bounds, double theta, float eps2)
 {
-    put_child(recs, pair, 1, REC_DUMMY_X, 0.f, 0.f, 0.f, 0.f, 0, 0, -1);
-}
-
-__device__ __forceinline__ void put_cell(float4* __restrict__ recs, int64_t pair, int comp, const D4& S, int level,
-                                         double bounds, double theta, float eps2, int first, int nchild)
-{
-    const double inv = S.w > 0.0 ? 1.0 / S.w : 0.0;
     // cell size = 2*bounds / 2^level; MAC  size/d < theta  <=>  d^2 > size^2/theta^2
     const double size = ldexp(2.0 * bounds, -level);
     float T = REC_T_MAX;
     if (theta > 0.0) T = fminf(fmaxf((float)fmin((size * size) / (theta * theta), 1e31), eps2), REC_T_MAX);
-    put_child(recs, pair, comp, (float)(S.x * inv), (float)(S.y * inv), (float)(S.z * inv), (float)S.w, T, first, nchild, -1);
+    return T;
 }
 
-__global__ void __launch_bounds__(256) write_records_kernel(const uint64_t* __restrict__ keys, int n,
-                                                            const int* __restrict__ childL, const int* __restrict__ childR,
-                                                            const int* __restrict__ parent, const int2* __restrict__ range,
-                                                            const D4* __restrict__ msum, const int* __restrict__ first,
-                                                            const int* __restrict__ nchild, const float4* __restrict__ posm,
-                                                            const double* __restrict__ bounds_p, double theta, float eps2,
-                                                            const int* __restrict__ root, float4* __restrict__ recs)
+__device__ __forceinline__ ChildRec cell_child(const D4& S, int level, double bounds, double theta, float eps2, int first,
+                                               int nchild)
+{
+    const double inv = S.w > 0.0 ? 1.0 / S.w : 0.0;
+    return ChildRec{(float)(S.x * inv), (float)(S.y * inv), (float)(S.z * inv), (float)S.w,
+                    cell_threshold(level, bounds, theta, eps2), first, nchild, -1};
+}
+
+__device__ __forceinline__ ChildRec load_child(int c, const D4* __restrict__ msum, const signed char* __restrict__ lvl,
+                                               const int* __restrict__ first, const int* __restrict__ nchild,
+                                               const float4* __restrict__ posm, double bounds, double theta, float eps2)
+{
+    if (c < 0) {
+        const int k = ~c;
+        const float4 b = posm[k];
+        return ChildRec{b.x, b.y, b.z, b.w, eps2, 0, 0, k};
+    }
+    const double2 a = *reinterpret_cast<const double2*>(&msum[c]);
+    const double2 b = *(reinterpret_cast<const double2*>(&msum[c]) + 1);
+    return cell_child(D4{a.x, a.y, b.x, b.y}, lvl[c], bounds, theta, eps2, first[c], nchild[c]);
+}
+
+__device__ __forceinline__ void store_pair(float4* __restrict__ recs, int64_t pair, const ChildRec& a, const ChildRec& b)
+{
+    float4* q = recs + 4 * pair;
+    q[0] = make_float4(a.x, b.x, a.y, b.y);
+    q[1] = make_float4(a.z, b.z, a.m, b.m);
+    q[2] = make_float4(a.T, b.T, __int_as_float(a.first), __int_as_float(b.first));
+    q[3] = make_float4(__int_as_float(a.nchild), __int_as_float(b.nchild), __int_as_float(a.body), __int_as_float(b.body));
+}
+
+__global__ void __launch_bounds__(256) write_records_kernel(int n, const int2* __restrict__ range, const D4* __restrict__ msum,
+                                                            const signed char* __restrict__ lvl, const int* __restrict__ first,
+                                                            const int* __restrict__ nchild, const int4* __restrict__ kids,
+                                                            const float4* __restrict__ posm, const double* __restrict__ bounds_p,
+                                                            double theta, float eps2, const int* __restrict__ root,
+                                                            float4* __restrict__ recs)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     const int nc = nchild[i];
     if (nc == 0) return;
     const double bounds = *bounds_p;
-    const int Li = level_of(cpl(keys, i, n));
-    if (i == *root) {   // pair 0 = {root cell, dummy}
-        put_cell(recs, 0, 0, msum[i], Li, bounds, theta, eps2, first[i], nc);
-        put_dummy(recs, 0);
-    }
+    const int Li = lvl[i];
     const int64_t base = first[i];
-    int c = 0;
-    for_each_octree_child(keys, n, childL, childR, range, i, Li, [&](int ch) {
-        const int64_t pair = base + (c >> 1);
-        if (ch < 0) {
-            const int k = ~ch;
-            const float4 b = posm[k];
-            put_child(recs, pair, c & 1, b.x, b.y, b.z, b.w, eps2, 0, 0, k);
-        } else {
-            put_cell(recs, pair, c & 1, msum[ch], level_of(cpl(keys, ch, n)), bounds, theta, eps2, first[ch], nchild[ch]);
+    if (i == *root)   // pair 0 = {root cell, dummy}
+        store_pair(recs, 0, cell_child(msum[i], Li, bounds, theta, eps2, (int)base, nc), dummy_child());
+    if (Li >= MORTON_LEVELS) {   // bucket: the leaves of the range
+        const int k0 = range[i].x;
+        for (int c = 0; c < nc; c += 2) {
+            const ChildRec a = load_child(~(k0 + c), msum, lvl, first, nchild, posm, bounds, theta, eps2);
+            const ChildRec b = (c + 1 < nc) ? load_child(~(k0 + c + 1), msum, lvl, first, nchild, posm, bounds, theta, eps2)
+                                            : dummy_child();
+            store_pair(recs, base + (c >> 1), a, b);
         }
-        ++c;
-    });
-    if (nc & 1) put_dummy(recs, base + (nc >> 1));
+        return;
+    }
+    const int4 k0 = kids[2 * (int64_t)i], k1 = kids[2 * (int64_t)i + 1];
+    const int kid[KIDS] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+    for (int c = 0; c < KIDS; c += 2) {
+        if (c < nc) {
+            const ChildRec a = load_child(kid[c], msum, lvl, first, nchild, posm, bounds, theta, eps2);
+            const ChildRec b = (c + 1 < nc) ? load_child(kid[c + 1], msum, lvl, first, nchild, posm, bounds, theta, eps2)
+                                            : dummy_child();
+            store_pair(recs, base + (c >> 1), a, b);
+        }
+    }
 }
 
 // single body: the root record is that leaf
 __global__ void single_body_record_kernel(const float4* __restrict__ posm, float eps2, float4* __restrict__ recs)
 {
     const float4 b = posm[0];
-    put_child(recs, 0, 0, b.x, b.y, b.z, b.w, eps2, 0, 0, 0);
-    put_dummy(recs, 0);
+    store_pair(recs, 0, ChildRec{b.x, b.y, b.z, b.w, eps2, 0, 0, 0}, dummy_child());
 }
 
 // ============================================================================ traversal
@@ -572,6 +613,8 @@ void nbody_alloc(NBodySim& s, int n)
     s.other = alloc_counted<int>(s, N);
     s.range = alloc_counted<int2>(s, N);
     s.msum = alloc_counted<D4>(s, N);
+    s.lvl = alloc_counted<signed char>(s, N);
+    s.kids = alloc_counted<int4>(s, 2 * N);
     s.first = alloc_counted<int>(s, N);
     s.nchild = alloc_counted<int>(s, N);
     // pair records: <= (children + cells) / 2 <= 1.5 N pairs, + the root pair
@@ -607,6 +650,7 @@ void nbody_free(NBodySim& s)
     s.sorter.destroy();
     cudaFree(s.posm); cudaFree(s.acc); cudaFree(s.childL); cudaFree(s.childR); cudaFree(s.parent);
     cudaFree(s.other); cudaFree(s.range); cudaFree(s.msum); cudaFree(s.first); cudaFree(s.nchild);
+    cudaFree(s.lvl); cudaFree(s.kids);
     cudaFree(s.recs); cudaFree(s.colors); cudaFree(s.stage); cudaFree(s.d_maxabs); cudaFree(s.d_bounds);
     cudaFree(s.d_children);
     cudaFree(s.d_root); cudaFree(s.d_alloc); cudaFree(s.d_tile_counter); cudaFree(s.d_interactions);
@@ -694,7 +738,7 @@ void nbody_build_tree(NBodySim& s)
     if (n > 1) {
         B200_CHECK(cudaMemsetAsync(s.other, 0xff, (size_t)n * sizeof(int), st));
         build_kernel<<<grid, 256, 0, st>>>(s.keys[s.sorted_slot], s.pos[s.cur], s.mass[s.cur], n, s.childL, s.childR,
-                                           s.parent, s.other, s.range, s.msum, s.d_root);
+                                           s.parent, s.other, s.range, s.msum, s.lvl, s.d_root);
         ++s.launches;
         B200_CHECK(cudaGetLastError());
     }
@@ -705,10 +749,10 @@ void nbody_build_tree(NBodySim& s)
         B200_CHECK(cudaMemcpyAsync(s.d_alloc, &s.h_one, sizeof(unsigned), cudaMemcpyHostToDevice, st));   // pair 0 is the root's
         B200_CHECK(cudaMemsetAsync(s.d_children, 0, sizeof(unsigned), st));
         const int g1 = div_up(n - 1, 256);
-        count_children_kernel<<<g1, 256, 0, st>>>(s.keys[s.sorted_slot], n, s.childL, s.childR, s.parent, s.range, s.first,
-                                                  s.nchild, s.d_alloc, (unsigned)s.rec_capacity, s.d_error, s.d_children);
-        write_records_kernel<<<g1, 256, 0, st>>>(s.keys[s.sorted_slot], n, s.childL, s.childR, s.parent, s.range, s.msum,
-                                                 s.first, s.nchild, s.posm, s.d_bounds, s.theta, eps2f, s.d_root, s.recs);
+        count_children_kernel<<<g1, 256, 0, st>>>(n, s.childL, s.childR, s.parent, s.range, s.lvl, s.first, s.nchild, s.kids,
+                                                  s.d_alloc, (unsigned)s.rec_capacity, s.d_error, s.d_children);
+        write_records_kernel<<<g1, 256, 0, st>>>(n, s.range, s.msum, s.lvl, s.first, s.nchild, s.kids, s.posm, s.d_bounds,
+                                                 s.theta, eps2f, s.d_root, s.recs);
         s.launches += 2;
     } else {
         single_body_record_kernel<<<1, 1, 0, st>>>(s.posm, eps2f, s.recs);

@@ -60,6 +60,8 @@ struct NBodySim {
     int2* range = nullptr;
     D4* msum = nullptr;
     int *first = nullptr, *nchild = nullptr;
+    signed char* lvl = nullptr;               // octree level of every binary node
+    int4* kids = nullptr;                     // per head: its <= 8 octree children (2 x int4)
     float4* recs = nullptr;
     int64_t rec_capacity = 0;
 
