@@ -96,61 +96,151 @@ __device__ __forceinline__ int level_of(int c)
     return l > MORTON_LEVELS ? MORTON_LEVELS : l;
 }
 
-__device__ __forceinline__ D4 ldcg_d4(const D4* p)
+// delta(i, j): common-prefix metric between sorted keys i and j (any distance apart), -1 outside
+// the array.  Equal keys are told apart by their positions (Karras 2012, section 4).
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, uint64_t ki, int i, int64_t j, int n)
 {
-    const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
-    const double2 b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    if (j < 0 || j >= n) return -1;
+    const uint64_t x = ki ^ keys[j];
+    if (x) return __clzll((long long)x);
+    return 64 + __clz((int)((unsigned)i ^ (unsigned)j));
+}
+
+// Karras (2012) binary radix tree: every internal node i in [0, n-2] finds its own key range and
+// split by binary search on delta -- independent threads, no atomics, no fences.  Node i covers
+// the sorted bodies [range.x, range.y] (i is one of the two ends); children are internal nodes
+// (>= 0) or leaves (~k).  Node 0 is the root.  lvl = octree level of the node's smallest cell.
+__global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict__ keys, int n, int* __restrict__ childL,
+                                                     int* __restrict__ childR, int* __restrict__ parent,
+                                                     int2* __restrict__ range, signed char* __restrict__ lvl)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const uint64_t ki = keys[i];
+    const int dr = delta(keys, ki, i, (int64_t)i + 1, n), dl = delta(keys, ki, i, (int64_t)i - 1, n);
+    const int d = dr > dl ? 1 : -1;
+    const int dmin = dr > dl ? dl : dr;
+    int64_t lmax = 2;
+    while (delta(keys, ki, i, i + lmax * d, n) > dmin) lmax <<= 1;
+    int64_t l = 0;
+    for (int64_t t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, ki, i, i + (l + t) * d, n) > dmin) l += t;
+    const int j = (int)(i + l * d);
+    const int dnode = delta(keys, ki, i, j, n);
+    int64_t sft = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, ki, i, i + (sft + t) * d, n) > dnode) sft += t;
+    } while (t > 1);
+    const int gamma = (int)(i + sft * d + (d < 0 ? -1 : 0));
+    const int lo = min(i, j), hi = max(i, j);
+    const int left = (lo == gamma) ? ~gamma : gamma;
+    const int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    childL[i] = left;
+    childR[i] = right;
+    if (left >= 0) parent[left] = i;
+    if (right >= 0) parent[right] = i;
+    if (i == 0) parent[0] = -1;
+    range[i] = make_int2(lo, hi);
+    lvl[i] = (signed char)level_of(dnode);
+}
+
+// Mass sums of every node = differences of a prefix sum over the sorted bodies of
+// (m x, m y, m z, m) in fp64 -- the bottom-up equivalent of the reference's running-mean COM
+// (nbody/simulation.py:160-167) with no tree walk.  The prefix is BLOCKED (1024 bodies per
+// block: ploc = prefix inside the block, bex = sum of all earlier blocks) so that small cells
+// difference small numbers: the cancellation error of a cell's sum is <= 1e-16 * (block sum)
+// for cells inside a block and 1e-16 * (global sum) / (>= 1024 bodies) otherwise, i.e. <= 1e-8
+// absolute on a centre of mass at the 50 M preset's scale, 4 orders below fp32 rounding.
+constexpr int PFX_BLOCK = 1024;
+
+__device__ __forceinline__ D4 d4_add(const D4& a, const D4& b) { return D4{a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w}; }
+__device__ __forceinline__ D4 d4_sub(const D4& a, const D4& b) { return D4{a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w}; }
+__device__ __forceinline__ D4 d4_shfl_up(const D4& v, int o)
+{
+    return D4{__shfl_up_sync(0xffffffffu, v.x, o), __shfl_up_sync(0xffffffffu, v.y, o), __shfl_up_sync(0xffffffffu, v.z, o),
+              __shfl_up_sync(0xffffffffu, v.w, o)};
+}
+__device__ __forceinline__ void d4_store(D4* p, const D4& v)
+{
+    reinterpret_cast<double2*>(p)[0] = make_double2(v.x, v.y);
+    reinterpret_cast<double2*>(p)[1] = make_double2(v.z, v.w);
+}
+__device__ __forceinline__ D4 d4_load(const D4* p)
+{
+    const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
     return D4{a.x, a.y, b.x, b.y};
 }
 
-// Bottom-up agglomerative construction (Apetrei 2014) of the Karras binary radix tree with
-// the mass / centre-of-mass reduction fused in: every leaf climbs; at each parent the first
-// arriver leaves its range end in other[] and stops, the second combines both children.
-// Internal node p sits at the split between sorted positions p and p+1.
-// Sums are carried as (sum m x, sum m y, sum m z, sum m) in fp64, the bottom-up equivalent
-// of the reference's running mean (nbody/simulation.py:160-167).
-__global__ void __launch_bounds__(256) build_kernel(const uint64_t* __restrict__ keys, const double* __restrict__ pos,
-                                                    const double* __restrict__ mass, int n,
-                                                    int* childL, int* childR, int* parent, int* other, int2* range,
-                                                    D4* msum, signed char* lvl, int* root)
+__global__ void __launch_bounds__(256) prefix_kernel(const double* __restrict__ pos, const double* __restrict__ mass, int n,
+                                                     D4* __restrict__ ploc, D4* __restrict__ btot)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const double m = mass[k];
-    D4 S{m * pos[3 * (int64_t)k], m * pos[3 * (int64_t)k + 1], m * pos[3 * (int64_t)k + 2], m};
-    int l = k, r = k, node = ~k;
-    for (;;) {
-        if (l == 0 && r == n - 1) {
-            *root = node;
-            if (node >= 0) parent[node] = -1;
-            break;
+    __shared__ D4 wtot[8];
+    const int64_t base = (int64_t)blockIdx.x * PFX_BLOCK + 4 * threadIdx.x;
+    D4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int64_t k = base + q;
+        if (k < n) {
+            const double m = mass[k];
+            v[q] = D4{m * pos[3 * k], m * pos[3 * k + 1], m * pos[3 * k + 2], m};
+        } else {
+            v[q] = D4{0.0, 0.0, 0.0, 0.0};
         }
-        const int cr = cpl(keys, r, n), cl = cpl(keys, l - 1, n);
-        const bool right = cr > cl;
-        const int p = right ? r : l - 1;
-        if (right) childL[p] = node; else childR[p] = node;
-        if (node >= 0) parent[node] = p;
-        __threadfence();
-        const int o = atomicExch(&other[p], right ? l : r);
-        if (o == -1) break;
-        __threadfence();
-        const int sib = __ldcg(right ? &childR[p] : &childL[p]);
-        D4 T;
-        if (sib >= 0) T = ldcg_d4(&msum[sib]);
-        else {
-            const int64_t kk = ~sib;
-            const double mm = mass[kk];
-            T = D4{mm * pos[3 * kk], mm * pos[3 * kk + 1], mm * pos[3 * kk + 2], mm};
-        }
-        // left + right, so the sum does not depend on which child arrived first
-        if (right) S = D4{S.x + T.x, S.y + T.y, S.z + T.z, S.w + T.w};
-        else       S = D4{T.x + S.x, T.y + S.y, T.z + S.z, T.w + S.w};
-        if (right) r = o; else l = o;
-        msum[p] = S;
-        range[p] = make_int2(l, r);
-        lvl[p] = (signed char)level_of(right ? cr : cl);   // the node's own prefix metric is the larger boundary one
-        node = p;
+        if (q) v[q] = d4_add(v[q - 1], v[q]);
     }
+    D4 inc = v[3];
+    for (int o = 1; o < 32; o <<= 1) {
+        const D4 t = d4_shfl_up(inc, o);
+        if (lane_id() >= (unsigned)o) inc = d4_add(t, inc);
+    }
+    const int warp = threadIdx.x >> 5;
+    if (lane_id() == 31) wtot[warp] = inc;
+    __syncthreads();
+    D4 off{0.0, 0.0, 0.0, 0.0};
+    for (int w = 0; w < warp; ++w) off = d4_add(off, wtot[w]);
+    const D4 excl = d4_add(off, d4_sub(inc, v[3]));
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (base + q < n) d4_store(&ploc[base + q], d4_add(excl, v[q]));
+    if (threadIdx.x == 255) d4_store(&btot[blockIdx.x], d4_add(excl, v[3]));
+}
+
+// exclusive scan of the block totals, in place (one CTA; <= 50 k blocks at 50 M bodies)
+__global__ void __launch_bounds__(1024) prefix_blocks_kernel(D4* __restrict__ btot, int nb)
+{
+    __shared__ D4 wtot[32];
+    __shared__ D4 carry_s;
+    if (threadIdx.x == 0) carry_s = D4{0.0, 0.0, 0.0, 0.0};
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        const int b = base + threadIdx.x;
+        const D4 v = b < nb ? d4_load(&btot[b]) : D4{0.0, 0.0, 0.0, 0.0};
+        D4 inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const D4 t = d4_shfl_up(inc, o);
+            if (lane_id() >= (unsigned)o) inc = d4_add(t, inc);
+        }
+        const int warp = threadIdx.x >> 5;
+        if (lane_id() == 31) wtot[warp] = inc;
+        __syncthreads();
+        D4 off = carry_s;
+        for (int w = 0; w < warp; ++w) off = d4_add(off, wtot[w]);
+        if (b < nb) d4_store(&btot[b], d4_add(off, d4_sub(inc, v)));
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = d4_add(off, inc);
+        __syncthreads();
+    }
+}
+
+// (sum m x, sum m y, sum m z, sum m) over the sorted bodies [l, r]
+__device__ __forceinline__ D4 segment_sum(const D4* __restrict__ ploc, const D4* __restrict__ bex, int l, int r)
+{
+    const int bl = l / PFX_BLOCK, br = r / PFX_BLOCK;
+    D4 S = d4_load(&ploc[r]);
+    if (l % PFX_BLOCK) S = d4_sub(S, d4_load(&ploc[l - 1]));
+    if (bl != br) S = d4_add(d4_sub(d4_load(&bex[br]), d4_load(&bex[bl])), S);
+    return S;
 }
 
 // ---------------------------------------------------------------------------- octree records
@@ -277,18 +367,25 @@ __device__ __forceinline__ ChildRec cell_child(const D4& S, int level, double bo
                     cell_threshold(level, bounds, theta, eps2), first, nchild, -1};
 }
 
-__device__ __forceinline__ ChildRec load_child(int c, const D4* __restrict__ msum, const signed char* __restrict__ lvl,
-                                               const int* __restrict__ first, const int* __restrict__ nchild,
-                                               const float4* __restrict__ posm, double bounds, double theta, float eps2)
+struct TreeView {
+    const int2* __restrict__ range;
+    const D4* __restrict__ ploc;
+    const D4* __restrict__ bex;
+    const signed char* __restrict__ lvl;
+    const int* __restrict__ first;
+    const int* __restrict__ nchild;
+    const float4* __restrict__ posm;
+};
+
+__device__ __forceinline__ ChildRec load_child(int c, const TreeView& tv, double bounds, double theta, float eps2)
 {
     if (c < 0) {
         const int k = ~c;
-        const float4 b = posm[k];
+        const float4 b = tv.posm[k];
         return ChildRec{b.x, b.y, b.z, b.w, eps2, 0, 0, k};
     }
-    const double2 a = *reinterpret_cast<const double2*>(&msum[c]);
-    const double2 b = *(reinterpret_cast<const double2*>(&msum[c]) + 1);
-    return cell_child(D4{a.x, a.y, b.x, b.y}, lvl[c], bounds, theta, eps2, first[c], nchild[c]);
+    const int2 rg = tv.range[c];
+    return cell_child(segment_sum(tv.ploc, tv.bex, rg.x, rg.y), tv.lvl[c], bounds, theta, eps2, tv.first[c], tv.nchild[c]);
 }
 
 __device__ __forceinline__ void store_pair(float4* __restrict__ recs, int64_t pair, const ChildRec& a, const ChildRec& b)
@@ -300,27 +397,25 @@ __device__ __forceinline__ void store_pair(float4* __restrict__ recs, int64_t pa
     q[3] = make_float4(__int_as_float(a.nchild), __int_as_float(b.nchild), __int_as_float(a.body), __int_as_float(b.body));
 }
 
-__global__ void __launch_bounds__(256) write_records_kernel(int n, const int2* __restrict__ range, const D4* __restrict__ msum,
-                                                            const signed char* __restrict__ lvl, const int* __restrict__ first,
-                                                            const int* __restrict__ nchild, const int4* __restrict__ kids,
-                                                            const float4* __restrict__ posm, const double* __restrict__ bounds_p,
-                                                            double theta, float eps2, const int* __restrict__ root,
+__global__ void __launch_bounds__(256) write_records_kernel(int n, TreeView tv, const int4* __restrict__ kids,
+                                                            const double* __restrict__ bounds_p, double theta, float eps2,
                                                             float4* __restrict__ recs)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
-    const int nc = nchild[i];
+    const int nc = tv.nchild[i];
     if (nc == 0) return;
     const double bounds = *bounds_p;
-    const int Li = lvl[i];
-    const int64_t base = first[i];
-    if (i == *root)   // pair 0 = {root cell, dummy}
-        store_pair(recs, 0, cell_child(msum[i], Li, bounds, theta, eps2, (int)base, nc), dummy_child());
+    const int Li = tv.lvl[i];
+    const int64_t base = tv.first[i];
+    if (i == 0)   // node 0 is the root; pair 0 = {root cell, dummy}
+        store_pair(recs, 0, cell_child(segment_sum(tv.ploc, tv.bex, 0, n - 1), Li, bounds, theta, eps2, (int)base, nc),
+                   dummy_child());
     if (Li >= MORTON_LEVELS) {   // bucket: the leaves of the range
-        const int k0 = range[i].x;
+        const int k0 = tv.range[i].x;
         for (int c = 0; c < nc; c += 2) {
-            const ChildRec a = load_child(~(k0 + c), msum, lvl, first, nchild, posm, bounds, theta, eps2);
-            const ChildRec b = (c + 1 < nc) ? load_child(~(k0 + c + 1), msum, lvl, first, nchild, posm, bounds, theta, eps2)
+            const ChildRec a = load_child(~(k0 + c), tv, bounds, theta, eps2);
+            const ChildRec b = (c + 1 < nc) ? load_child(~(k0 + c + 1), tv, bounds, theta, eps2)
                                             : dummy_child();
             store_pair(recs, base + (c >> 1), a, b);
         }
@@ -331,8 +426,8 @@ __global__ void __launch_bounds__(256) write_records_kernel(int n, const int2* _
 #pragma unroll
     for (int c = 0; c < KIDS; c += 2) {
         if (c < nc) {
-            const ChildRec a = load_child(kid[c], msum, lvl, first, nchild, posm, bounds, theta, eps2);
-            const ChildRec b = (c + 1 < nc) ? load_child(kid[c + 1], msum, lvl, first, nchild, posm, bounds, theta, eps2)
+            const ChildRec a = load_child(kid[c], tv, bounds, theta, eps2);
+            const ChildRec b = (c + 1 < nc) ? load_child(kid[c + 1], tv, bounds, theta, eps2)
                                             : dummy_child();
             store_pair(recs, base + (c >> 1), a, b);
         }
@@ -610,9 +705,9 @@ void nbody_alloc(NBodySim& s, int n)
     s.childL = alloc_counted<int>(s, N);
     s.childR = alloc_counted<int>(s, N);
     s.parent = alloc_counted<int>(s, N);
-    s.other = alloc_counted<int>(s, N);
     s.range = alloc_counted<int2>(s, N);
-    s.msum = alloc_counted<D4>(s, N);
+    s.ploc = alloc_counted<D4>(s, N);
+    s.bex = alloc_counted<D4>(s, N / PFX_BLOCK + 2);
     s.lvl = alloc_counted<signed char>(s, N);
     s.kids = alloc_counted<int4>(s, 2 * N);
     s.first = alloc_counted<int>(s, N);
@@ -649,7 +744,7 @@ void nbody_free(NBodySim& s)
     }
     s.sorter.destroy();
     cudaFree(s.posm); cudaFree(s.acc); cudaFree(s.childL); cudaFree(s.childR); cudaFree(s.parent);
-    cudaFree(s.other); cudaFree(s.range); cudaFree(s.msum); cudaFree(s.first); cudaFree(s.nchild);
+    cudaFree(s.range); cudaFree(s.ploc); cudaFree(s.bex); cudaFree(s.first); cudaFree(s.nchild);
     cudaFree(s.lvl); cudaFree(s.kids);
     cudaFree(s.recs); cudaFree(s.colors); cudaFree(s.stage); cudaFree(s.d_maxabs); cudaFree(s.d_bounds);
     cudaFree(s.d_children);
@@ -734,12 +829,13 @@ void nbody_build_tree(NBodySim& s)
     B200_CHECK(cudaGetLastError());
     s.cur = o;
     s.timer.mark(st);
-    // ---- binary radix tree + mass/COM
+    // ---- binary radix tree (Karras) + blocked prefix sums of (m x, m y, m z, m)
     if (n > 1) {
-        B200_CHECK(cudaMemsetAsync(s.other, 0xff, (size_t)n * sizeof(int), st));
-        build_kernel<<<grid, 256, 0, st>>>(s.keys[s.sorted_slot], s.pos[s.cur], s.mass[s.cur], n, s.childL, s.childR,
-                                           s.parent, s.other, s.range, s.msum, s.lvl, s.d_root);
-        ++s.launches;
+        karras_kernel<<<div_up(n - 1, 256), 256, 0, st>>>(s.keys[s.sorted_slot], n, s.childL, s.childR, s.parent, s.range, s.lvl);
+        const int nb = div_up(n, PFX_BLOCK);
+        prefix_kernel<<<nb, 256, 0, st>>>(s.pos[s.cur], s.mass[s.cur], n, s.ploc, s.bex);
+        prefix_blocks_kernel<<<1, 1024, 0, st>>>(s.bex, nb);
+        s.launches += 3;
         B200_CHECK(cudaGetLastError());
     }
     s.timer.mark(st);
@@ -751,8 +847,8 @@ void nbody_build_tree(NBodySim& s)
         const int g1 = div_up(n - 1, 256);
         count_children_kernel<<<g1, 256, 0, st>>>(n, s.childL, s.childR, s.parent, s.range, s.lvl, s.first, s.nchild, s.kids,
                                                   s.d_alloc, (unsigned)s.rec_capacity, s.d_error, s.d_children);
-        write_records_kernel<<<g1, 256, 0, st>>>(n, s.range, s.msum, s.lvl, s.first, s.nchild, s.kids, s.posm, s.d_bounds,
-                                                 s.theta, eps2f, s.d_root, s.recs);
+        const TreeView tv{s.range, s.ploc, s.bex, s.lvl, s.first, s.nchild, s.posm};
+        write_records_kernel<<<g1, 256, 0, st>>>(n, tv, s.kids, s.d_bounds, s.theta, eps2f, s.recs);
         s.launches += 2;
     } else {
         single_body_record_kernel<<<1, 1, 0, st>>>(s.posm, eps2f, s.recs);

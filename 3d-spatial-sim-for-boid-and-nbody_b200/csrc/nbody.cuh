@@ -11,7 +11,8 @@
 //   keys[2]/vals[2]  63-bit Morton keys + permutation, radix-sort ping-pong
 //   posm       (N) float4 {x,y,z,m} of the sorted bodies (traversal targets / leaf records)
 //   binary radix tree over the sorted keys (N-1 internal nodes): childL/childR/parent,
-//                range, msum = (sum m x, sum m y, sum m z, sum m) in f64
+//                range, lvl; ploc/bex = blocked fp64 prefix sums of (m x, m y, m z, m) over the
+//                sorted bodies, so any node's mass / centre of mass is a difference of two entries
 //   recs       octree "pair records", 64 B each = 4 x float4, holding children 2j and 2j+1 of
 //              a cell side by side for packed fp32x2 math:
 //                {x0,x1,y0,y1} {z0,z1,m0,m1} {T0,T1,first0,first1} {nchild0,nchild1,body0,body1}
@@ -56,9 +57,9 @@ struct NBodySim {
 
     float4* posm = nullptr;
     float4* acc = nullptr;
-    int *childL = nullptr, *childR = nullptr, *parent = nullptr, *other = nullptr;
+    int *childL = nullptr, *childR = nullptr, *parent = nullptr;
     int2* range = nullptr;
-    D4* msum = nullptr;
+    D4 *ploc = nullptr, *bex = nullptr;       // blocked fp64 prefix sums of (m x, m y, m z, m)
     int *first = nullptr, *nchild = nullptr;
     signed char* lvl = nullptr;               // octree level of every binary node
     int4* kids = nullptr;                     // per head: its <= 8 octree children (2 x int4)
