@@ -41,15 +41,17 @@ inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
-__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p)
+// gpu-scope relaxed accesses for flag+value status words (ld.volatile compiles to a system-scope
+// strong load, which is slower than the look-back needs)
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p)
 {
     unsigned v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_volatile_u32(unsigned* p, unsigned v)
+__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v)
 {
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // Phase timer: CUDA events on the launching stream, accumulated per phase when enabled.

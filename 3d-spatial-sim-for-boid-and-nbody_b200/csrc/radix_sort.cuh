@@ -36,15 +36,26 @@ __global__ void __launch_bounds__(BLOCK) hist_kernel(const K* __restrict__ keys,
     __shared__ unsigned sh[MAX_PASSES * RADIX];
     for (int i = threadIdx.x; i < npass * RADIX; i += BLOCK) sh[i] = 0;
     __syncthreads();
-    const int stride = gridDim.x * BLOCK;
-    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += stride) {
-        const K k = keys[i];
-        for (int p = 0; p < npass; ++p) {
-            const unsigned d = (unsigned)(k >> (begin_bit + 8 * p)) & 255u;
-            // nearly-sorted input makes whole warps hit one bin in the high digits:
-            // aggregate equal digits in the warp before touching shared memory.
-            const unsigned peers = __match_any_sync(__activemask(), d);
-            if ((peers & lanemask_lt()) == 0) atomicAdd(&sh[p * RADIX + d], (unsigned)__popc(peers));
+    // whole warps walk the keys 32 at a time.  The input is nearly sorted (last step's order), so
+    // in the high digits all 32 lanes usually share one bin: one +32 instead of 32 conflicting
+    // atomics; low digits are close to random and conflict-free.
+    const int64_t nwarps = (int64_t)gridDim.x * (BLOCK / 32);
+    for (int64_t w = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5); w * 32 < n; w += nwarps) {
+        const int64_t i = w * 32 + lane_id();
+        if (w * 32 + 32 <= n) {
+            const K k = keys[i];
+            for (int p = 0; p < npass; ++p) {
+                const unsigned d = (unsigned)(k >> (begin_bit + 8 * p)) & 255u;
+                const unsigned d0 = __shfl_sync(0xffffffffu, d, 0);
+                if (__all_sync(0xffffffffu, d == d0)) {
+                    if (lane_id() == 0) atomicAdd(&sh[p * RADIX + d0], 32u);
+                } else {
+                    atomicAdd(&sh[p * RADIX + d], 1u);
+                }
+            }
+        } else if (i < n) {
+            const K k = keys[i];
+            for (int p = 0; p < npass; ++p) atomicAdd(&sh[p * RADIX + ((unsigned)(k >> (begin_bit + 8 * p)) & 255u)], 1u);
         }
     }
     __syncthreads();
@@ -92,6 +103,7 @@ __global__ void __launch_bounds__(BLOCK) onesweep_kernel(const K* __restrict__ k
     const unsigned lane = lane_id();
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);   // dynamic tile order => predecessors are already running
     for (int i = tid; i < WARPS * RADIX; i += BLOCK) (&warp_hist[0][0])[i] = 0;
+    tile_off[tid] = 0;                              // doubles as the tile's early digit histogram
     __syncthreads();
     const unsigned tile = s_tile;
     const int64_t base = (int64_t)tile * TILE;
@@ -106,49 +118,49 @@ __global__ void __launch_bounds__(BLOCK) onesweep_kernel(const K* __restrict__ k
         const int t = woff + j * 32;
         key[j] = (t < valid) ? keys_in[base + t] : (K)~(K)0;   // padding sorts to the tile's end
     }
-    // ---- rank inside (warp, digit) with match-any
-    const unsigned lt = lanemask_lt();
+    // ---- early digit counts of the tile, published at once so successors never wait on our ranking
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         const unsigned d = (unsigned)(key[j] >> shift) & 255u;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(peers) - 1;
-        unsigned prev = 0;
-        if ((int)lane == leader) {
-            prev = warp_hist[warp][d];
-            warp_hist[warp][d] = prev + __popc(peers);
+        const unsigned d0 = __shfl_sync(0xffffffffu, d, 0);
+        if (__all_sync(0xffffffffu, d == d0)) {
+            if (lane == 0) atomicAdd(&tile_off[d0], 32u);
+        } else {
+            atomicAdd(&tile_off[d], 1u);
         }
+    }
+    __syncthreads();
+    const int d = tid;
+    const unsigned count = tile_off[d];
+    unsigned* st = status + (size_t)tile * RADIX + d;
+    st_relaxed_u32(st, (tile > 0 ? FLAG_AGG : FLAG_INC) | count);
+
+    // ---- rank inside (warp, digit): all match-any first (independent), then the running counters
+    const unsigned lt = lanemask_lt();
+    unsigned peers[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) peers[j] = __match_any_sync(0xffffffffu, (unsigned)(key[j] >> shift) & 255u);
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const unsigned dj = (unsigned)(key[j] >> shift) & 255u;
+        const int leader = __ffs(peers[j]) - 1;
+        unsigned prev = 0;
+        if ((int)lane == leader) prev = atomicAdd(&warp_hist[warp][dj], (unsigned)__popc(peers[j]));
         prev = __shfl_sync(0xffffffffu, prev, leader);
-        rank[j] = prev + __popc(peers & lt);
-        __syncwarp();
+        rank[j] = prev + __popc(peers[j] & lt);
     }
     __syncthreads();
 
-    // ---- per-digit: exclusive offsets of each warp, tile total, decoupled look-back
-    const int d = tid;
-    unsigned count = 0;
+    // ---- per digit: exclusive offsets of each warp; exclusive scan of the tile's digit counts
+    {
+        unsigned run = 0;
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) {
-        const unsigned t = warp_hist[w][d];
-        warp_hist[w][d] = count;
-        count += t;
-    }
-    unsigned excl = 0;
-    unsigned* st = status + (size_t)tile * RADIX + d;
-    if (tile > 0) {
-        st_volatile_u32(st, FLAG_AGG | count);
-        const unsigned* look = st - RADIX;
-        for (;;) {
-            const unsigned s = ld_volatile_u32(look);
-            if ((s & FLAG_MASK) == 0) continue;
-            excl += s & VAL_MASK;
-            if (s & FLAG_INC) break;
-            look -= RADIX;
+        for (int w = 0; w < WARPS; ++w) {
+            const unsigned t = warp_hist[w][d];
+            warp_hist[w][d] = run;
+            run += t;
         }
     }
-    st_volatile_u32(st, FLAG_INC | (excl + count));
-
-    // ---- exclusive scan of the tile's digit counts
     unsigned inc = count;
     for (int o = 1; o < 32; o <<= 1) {
         const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -160,7 +172,6 @@ __global__ void __launch_bounds__(BLOCK) onesweep_kernel(const K* __restrict__ k
     for (int w = 0; w < warp; ++w) wbase += wsum[w];
     const unsigned toff = wbase + inc - count;
     tile_off[d] = toff;
-    gbase[d] = digit_start[d] + excl - toff;
     __syncthreads();
 
     // ---- stage keys and values in sorted order
@@ -179,6 +190,21 @@ __global__ void __launch_bounds__(BLOCK) onesweep_kernel(const K* __restrict__ k
         else v = (t < valid) ? vals_in[base + t] : 0u;
         svals[rank[j]] = v;
     }
+
+    // ---- decoupled look-back for digit d (after the staging, so the wait overlaps useful work)
+    unsigned excl = 0;
+    if (tile > 0) {
+        const unsigned* look = st - RADIX;
+        for (;;) {
+            const unsigned s = ld_relaxed_u32(look);
+            if ((s & FLAG_MASK) == 0) continue;
+            excl += s & VAL_MASK;
+            if (s & FLAG_INC) break;
+            look -= RADIX;
+        }
+        st_relaxed_u32(st, FLAG_INC | (excl + count));
+    }
+    gbase[d] = digit_start[d] + excl - toff;
     __syncthreads();
 
     // ---- coalesced runs out
