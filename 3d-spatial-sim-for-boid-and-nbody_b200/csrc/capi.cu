@@ -200,16 +200,20 @@ B200_API int b200_nbody_get_stats(b200_nbody* h, b200_nbody_stats* out)
         out->n = s.n;
         out->steps = s.steps;
         unsigned alloc = 0, err = 0;
-        unsigned long long inter = 0;
+        unsigned long long ctr[b200::TRAV_COUNTERS] = {0};
         B200_CHECK(cudaMemcpy(&alloc, s.d_alloc, sizeof(alloc), cudaMemcpyDeviceToHost));
         B200_CHECK(cudaMemcpy(&err, s.d_error, sizeof(err), cudaMemcpyDeviceToHost));
-        B200_CHECK(cudaMemcpy(&inter, s.d_interactions, sizeof(inter), cudaMemcpyDeviceToHost));
+        B200_CHECK(cudaMemcpy(ctr, s.d_interactions, sizeof(ctr), cudaMemcpyDeviceToHost));
         B200_CHECK(cudaMemcpy(&out->bounds, s.d_bounds, sizeof(double), cudaMemcpyDeviceToHost));
         unsigned kids = 0;
         B200_CHECK(cudaMemcpy(&kids, s.d_children, sizeof(kids), cudaMemcpyDeviceToHost));
         out->records = s.n > 1 ? (int64_t)kids + 1 : s.n;   // root + every cell's children
         out->pair_records = s.n > 1 ? (int64_t)alloc : 1;
-        out->interactions = (int64_t)inter;
+        out->interactions = (int64_t)ctr[0];
+        out->trav_pair_slots = (int64_t)ctr[1];
+        out->trav_lane_pairs = (int64_t)ctr[2];
+        out->trav_batches = (int64_t)ctr[3];
+        out->trav_stack_max = (int64_t)ctr[4];
         out->error_flags = err;
         out->sm_count = s.sm_count;
         out->bytes_allocated = (int64_t)s.bytes_allocated;
@@ -225,7 +229,7 @@ B200_API int b200_nbody_reset_stats(b200_nbody* h)
         b200::NBodySim& s = h->sim;
         B200_CHECK(cudaSetDevice(s.device));
         B200_CHECK(cudaStreamSynchronize(s.stream));
-        B200_CHECK(cudaMemset(s.d_interactions, 0, sizeof(unsigned long long)));
+        B200_CHECK(cudaMemset(s.d_interactions, 0, b200::TRAV_COUNTERS * sizeof(unsigned long long)));
         s.timer.reset();
     })
 }

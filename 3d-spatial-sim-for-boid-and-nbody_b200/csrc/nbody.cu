@@ -335,8 +335,9 @@ __global__ void __launch_bounds__(256) count_children_kernel(int n, const int* _
 
 // Pair records: children 2j and 2j+1 of a cell share one 64-byte record laid out for packed
 // fp32x2 math in the traversal (component c = child & 1):
-//   q0 = {x0, x1, y0, y1}   q1 = {z0, z1, m0, m1}   q2 = {T0, T1, first0, first1}
-//   q3 = {nchild0, nchild1, body0, body1}
+//   q0 = {x0, x1, y0, y1}   q1 = {z0, z1, m0, m1}   q2 = {T0, T1, -, -}
+//   q3 = {first0, first1, nchild0, nchild1}
+// (q2.z is where the traversal's staging copy carries the pair's lane mask)
 // T = max(size^2/theta^2, eps^2) for a cell (clamped to REC_T_MAX; theta = 0 => REC_T_MAX, "always
 // open"), eps^2 for a leaf.  An odd child count is padded with a massless dummy far away.
 constexpr float REC_T_MAX = 1e30f;        // above any real squared distance, below the sentinels'
@@ -393,8 +394,8 @@ __device__ __forceinline__ void store_pair(float4* __restrict__ recs, int64_t pa
     float4* q = recs + 4 * pair;
     q[0] = make_float4(a.x, b.x, a.y, b.y);
     q[1] = make_float4(a.z, b.z, a.m, b.m);
-    q[2] = make_float4(a.T, b.T, __int_as_float(a.first), __int_as_float(b.first));
-    q[3] = make_float4(__int_as_float(a.nchild), __int_as_float(b.nchild), __int_as_float(a.body), __int_as_float(b.body));
+    q[2] = make_float4(a.T, b.T, 0.f, 0.f);
+    q[3] = make_float4(__int_as_float(a.first), __int_as_float(b.first), __int_as_float(a.nchild), __int_as_float(b.nchild));
 }
 
 __global__ void __launch_bounds__(256) write_records_kernel(int n, TreeView tv, const int4* __restrict__ kids,
@@ -442,24 +443,42 @@ __global__ void single_body_record_kernel(const float4* __restrict__ posm, float
 }
 
 // ============================================================================ traversal
-// One warp owns 32 consecutive sorted bodies (one per lane).  The warp walks the octree with
-// a shared stack in shared memory whose entries are (child block, child count, lane mask):
-// only cells that some lane must OPEN are pushed, with the mask of exactly those lanes, so
-// every lane makes the reference's own per-body MAC decision (nbody/simulation.py:256-258) --
-// no group MAC.  Opening a cell loads its contiguous pair records with one coalesced
-// 16 B/lane load into a per-warp staging buffer; the children are then evaluated TWO per
-// iteration from shared-memory broadcasts with Blackwell's packed fp32x2 instructions
-// (FADD2/FMUL2/FFMA2, sm_100+):
-//   d2 = |com - p|^2 + eps^2;   open iff d2 <= T;   otherwise a += m (com - p) d2^-3/2
-// with T = max(size^2/theta^2, eps^2) (leaf: eps^2).  This is the reference's "accept iff
-// size/d < theta, add iff d^2 > eps^2" (:258-267): for size^2/theta^2 >= eps^2 the tests
-// coincide; otherwise the cell is always accepted and only d2 == eps^2 (zero distance: the
-// body itself) is excluded -- it "opens" nothing because leaves have no children.
-// Lanes outside an entry's mask take x = 1e18: d2 ~ 1e36 > T, so they never open, and their
+// One warp owns 32 consecutive sorted bodies (one per lane) and walks the octree for all of them
+// at once.  Work is organised in BATCHES so that the tree-walk bookkeeping is done by 32 lanes in
+// parallel and the inner loop is nothing but arithmetic:
+//   select  pop as many entries (cell's child block, pair count, lane mask) from the warp's stack
+//           as fit 32 pair slots (one lane per entry + a warp prefix sum)
+//   load    the pair records of all selected cells: coalesced 16 B/lane loads, staged in shared
+//           memory as SoA {x0,x1,y0,y1} {z0,z1,m0,m1} {T0,T1,mask} {first0,first1,n0,n1}
+//   eval    every lane evaluates every staged pair, TWO children per iteration with Blackwell's
+//           packed fp32x2 instructions (FADD2/FMUL2/FFMA2, sm_100+) from shared-memory broadcasts:
+//             d2 = |com - p|^2 + eps^2;   open iff d2 <= T;   otherwise a += m (com - p) d2^-3/2
+//           lane 0 records the two ballots of "open" per pair
+//   expand  lane j turns pair j's ballots into new stack entries (cells with children that some
+//           lane must open, with the mask of exactly those lanes) -- a ballot/popc prefix sum
+// T = max(size^2/theta^2, eps^2) (leaf: eps^2).  This is the reference's "accept iff
+// size/d < theta, add iff d^2 > eps^2" (nbody/simulation.py:252-267): for size^2/theta^2 >= eps^2
+// the tests coincide; otherwise the cell is always accepted and only d2 == eps^2 (zero distance:
+// the body itself) is excluded -- it "opens" nothing because leaves have no children.
+// Every lane makes the reference's own per-body MAC decision; there is no group MAC.  Lanes
+// outside a pair's mask take x = 1e18: d2 ~ 1e36 > T, so they never open, and their
 // "contribution" m * d2^-3/2 underflows to exactly 0; no per-child mask logic is needed.
-// The kernel is instruction-issue bound (ncu: ~90 % issue-slot utilisation), so the inner loop
-// is written for instruction count.  acc.w carries the lane's child evaluations (a cost proxy
-// for load balancing); with COUNT it is the exact interaction count = evaluations - opens.
+// The stack is depth-first in batches: while it holds more than TRAV_DFS_MARK entries only the
+// top entry is popped per batch, which bounds it by MARK + 64 + 7 * 21 < TRAV_CAP.
+struct __align__(16) WarpShared {
+    unsigned stk_first[TRAV_CAP];        // first pair of the child block | (pairs - 1) << 29
+    unsigned stk_mask[TRAV_CAP];         // lanes that must open the cell
+    // XY[32] ZM[32] TM[32] FN[32] OP[32]; areas are TRAV_AREA = 34 entries apart so that the four
+    // 16-byte quarters of a pair record, stored by four neighbouring lanes, fall in different banks
+    float4 stage[5 * TRAV_AREA];
+    unsigned d_first[TRAV_BATCH];        // pair slot -> global pair index
+    unsigned d_mask[TRAV_BATCH];         //           -> lane mask
+};
+static_assert(sizeof(WarpShared) % 16 == 0, "WarpShared must keep float4 alignment");
+constexpr size_t TRAV_SMEM_BYTES = sizeof(WarpShared) * TRAV_WARPS;
+constexpr unsigned TRAV_FIRST_MASK = (1u << 29) - 1u;
+constexpr int TRAV_CHUNK_PAIRS = 8;      // an entry holds <= 8 pairs (3 bits); larger buckets are split
+
 __device__ __forceinline__ float rsqrt_approx(float x)
 {
     float r;
@@ -468,19 +487,24 @@ __device__ __forceinline__ float rsqrt_approx(float x)
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const float4* __restrict__ recs, const float4* __restrict__ posm,
-                                                              float4* __restrict__ acc, int tile_begin, int tile_end, int n,
-                                                              float eps2, float G, unsigned* tile_counter,
-                                                              unsigned long long* interactions, unsigned* error)
+__global__ void __launch_bounds__(TRAV_BLOCK, 4) traverse_kernel(const float4* __restrict__ recs, const float4* __restrict__ posm,
+                                                                 float4* __restrict__ acc, int tile_begin, int tile_end, int n,
+                                                                 float eps2, float G, unsigned* tile_counter,
+                                                                 unsigned long long* counters, unsigned* error)
 {
-    __shared__ uint4 s_stack[TRAV_WARPS][TRAV_STACK];
-    __shared__ float4 s_stage[TRAV_WARPS][2 * TRAV_STAGE];
+    extern __shared__ __align__(16) unsigned char trav_smem[];
     const unsigned lane = lane_id();
-    const int warp = threadIdx.x >> 5;
-    uint4* stack = s_stack[warp];
-    float4* stage = s_stage[warp];
-    unsigned long long wcount = 0;
+    const unsigned lanebit = 1u << lane;
+    const unsigned lt = lanemask_lt();
+    WarpShared& ws = reinterpret_cast<WarpShared*>(trav_smem)[threadIdx.x >> 5];
+    const float4* sXY = ws.stage;
+    const float4* sZM = ws.stage + TRAV_AREA;
+    const float4* sTM = ws.stage + 2 * TRAV_AREA;
+    const float4* sFN = ws.stage + 3 * TRAV_AREA;
+    uint4* sOP = reinterpret_cast<uint4*>(ws.stage + 4 * TRAV_AREA);   // .x/.y = ballots of "open", child 0 / 1
     const float2 eps22 = make_float2(eps2, eps2);
+    unsigned long long w_inter = 0, w_slots = 0, w_lanepairs = 0, w_batches = 0;
+    int w_spmax = 0;
 
     for (;;) {
         unsigned t = 0;
@@ -493,78 +517,151 @@ __global__ void __launch_bounds__(TRAV_BLOCK) traverse_kernel(const float4* __re
         const float4 p = valid ? posm[k] : make_float4(0.f, 0.f, 0.f, 0.f);
         const float2 npy = make_float2(-p.y, -p.y), npz = make_float2(-p.z, -p.z);
         float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;   // (even, odd) children accumulate separately
-        int evals = 0, opens = 0;
+        int cnt = 0, lanepairs = 0, slots = 0;
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-        int sp = 0;
-        if (lane == 0) stack[0] = make_uint4(0u, 1u, vmask, 0u);
-        sp = 1;
+        if (lane == 0) { ws.stk_first[0] = 0u; ws.stk_mask[0] = vmask; }   // pair 0 = {root, dummy}
+        int sp = 1;
         __syncwarp();
         while (sp > 0) {
-            const uint4 e = stack[--sp];
-            const int first = (int)e.x;
-            int nch = (int)e.y;
-            __syncwarp();
-            if (nch > TRAV_STAGE) {   // rare (bucket of coincident bodies): leave the remainder on the stack
-                if (lane == 0) stack[sp] = make_uint4(e.x + TRAV_STAGE / 2, e.y - TRAV_STAGE, e.z, 0u);
-                ++sp;
-                nch = TRAV_STAGE;
+            // ---- select: lane l looks at the l-th entry from the top
+            const int idx = sp - 1 - (int)lane;
+            unsigned ef = 0, em = 0;
+            int np = 0;
+            if (idx >= 0) { ef = ws.stk_first[idx]; em = ws.stk_mask[idx]; np = (int)(ef >> 29) + 1; }
+            int incl = np;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += u;
             }
-            const int npairs = (nch + 1) >> 1;
-            if ((int)lane < 4 * npairs) stage[lane] = __ldg(&recs[4 * (int64_t)first + lane]);
-            const bool in = (e.z >> lane) & 1u;
-            const float qx = in ? p.x : REC_LANE_SENTINEL;
-            const float2 nqx = make_float2(-qx, -qx);
-            if (in) evals += nch;
+            const int limit = sp > TRAV_DFS_MARK ? 1 : 32;
+            const bool take = idx >= 0 && incl <= TRAV_BATCH && (int)lane < limit;
+            const int E = __popc(__ballot_sync(0xffffffffu, take));   // take is a prefix of the lanes; E >= 1
+            // (the max-reduce leaves P in a uniform register: the loops below are provably convergent)
+            const int P = __reduce_max_sync(0xffffffffu, (int)lane == E - 1 ? incl : 0);
+            sp -= E;
+            if ((int)lane < E) {
+                const int base = incl - np;
+                const unsigned f = ef & TRAV_FIRST_MASK;
+                for (int q = 0; q < np; ++q) { ws.d_first[base + q] = f + q; ws.d_mask[base + q] = em; }
+            }
             __syncwarp();
-            for (int j = 0; j < npairs; ++j) {
-                const float4 XY = stage[4 * j];
-                const float4 ZM = stage[4 * j + 1];
-                const float2 T = *reinterpret_cast<const float2*>(&stage[4 * j + 2]);
-                const float2 dx = __fadd2_rn(make_float2(XY.x, XY.y), nqx);
+            // ---- load: 8 pair records (4 x 16 B each) per warp-wide load
+#pragma unroll
+            for (int it = 0; it < TRAV_BATCH / 8; ++it) {
+                const int slot = it * 8 + (int)(lane >> 2);
+                if (slot < P) {
+                    float4 v = __ldg(&recs[4 * (int64_t)ws.d_first[slot] + (lane & 3u)]);
+                    if ((lane & 3u) == 2u) v.z = __uint_as_float(ws.d_mask[slot]);
+                    ws.stage[(lane & 3u) * TRAV_AREA + slot] = v;
+                }
+            }
+            __syncwarp();
+            // ---- eval
+#pragma unroll 4
+            for (int j = 0; j < P; ++j) {
+                const float4 XY = sXY[j];
+                const float4 ZM = sZM[j];
+                const float4 TM = sTM[j];
+                const bool in = (__float_as_uint(TM.z) & lanebit) != 0u;
+                const float nqx = in ? -p.x : -REC_LANE_SENTINEL;
+                const float2 dx = __fadd2_rn(make_float2(XY.x, XY.y), make_float2(nqx, nqx));
                 const float2 dy = __fadd2_rn(make_float2(XY.z, XY.w), npy);
                 const float2 dz = __fadd2_rn(make_float2(ZM.x, ZM.y), npz);
                 const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, eps22)));
-                const bool o0 = d2.x <= T.x, o1 = d2.y <= T.y;
+                const bool o0 = d2.x <= TM.x, o1 = d2.y <= TM.y;
                 const unsigned om0 = __ballot_sync(0xffffffffu, o0);
                 const unsigned om1 = __ballot_sync(0xffffffffu, o1);
+                if (lane == 0) *reinterpret_cast<uint2*>(&sOP[j]) = make_uint2(om0, om1);
                 float2 r;
                 r.x = o0 ? 0.f : rsqrt_approx(d2.x);
                 r.y = o1 ? 0.f : rsqrt_approx(d2.y);
                 if (COUNT) {
-                    if (o0) ++opens;
-                    if (o1) ++opens;
+                    if (in) {
+                        ++lanepairs;
+                        if (!o0 && XY.x < 2e18f) ++cnt;
+                        if (!o1 && XY.y < 2e18f) ++cnt;
+                    }
                 }
                 const float2 f = __fmul2_rn(make_float2(ZM.z, ZM.w), __fmul2_rn(__fmul2_rn(r, r), r));
                 ax = __ffma2_rn(dx, f, ax);
                 ay = __ffma2_rn(dy, f, ay);
                 az = __ffma2_rn(dz, f, az);
-                if (om0 | om1) {
-                    const float4 M2 = stage[4 * j + 2];
-                    const float4 M3 = stage[4 * j + 3];
-                    const unsigned nc0 = __float_as_uint(M3.x), nc1 = __float_as_uint(M3.y);
-                    if (sp >= TRAV_STACK - 2) {   // cannot happen for a 21-level tree; never drop silently
-                        if (lane == 0) atomicOr(error, (unsigned)ERR_STACK_OVERFLOW);
-                    } else {
-                        if (om0 && nc0) {
-                            if (lane == 0) stack[sp] = make_uint4(__float_as_uint(M2.z), nc0, om0, 0u);
-                            ++sp;
-                        }
-                        if (om1 && nc1) {
-                            if (lane == 0) stack[sp] = make_uint4(__float_as_uint(M2.w), nc1, om1, 0u);
-                            ++sp;
-                        }
+            }
+            slots += P;
+            __syncwarp();
+            // ---- expand: lane j owns pair slot j
+            bool c0 = false, c1 = false;
+            unsigned f0 = 0, f1 = 0, n0 = 0, n1 = 0;
+            uint2 om = make_uint2(0u, 0u);
+            if ((int)lane < P) {
+                om = *reinterpret_cast<const uint2*>(&sOP[lane]);
+                const float4 fn = sFN[lane];
+                f0 = __float_as_uint(fn.x); f1 = __float_as_uint(fn.y);
+                n0 = __float_as_uint(fn.z); n1 = __float_as_uint(fn.w);
+                c0 = om.x != 0u && n0 != 0u;
+                c1 = om.y != 0u && n1 != 0u;
+            }
+            const int np0 = (int)((n0 + 1u) >> 1), np1 = (int)((n1 + 1u) >> 1);
+            const bool big = (c0 && np0 > TRAV_CHUNK_PAIRS) || (c1 && np1 > TRAV_CHUNK_PAIRS);
+            if (!__any_sync(0xffffffffu, big)) {
+                const unsigned b0 = __ballot_sync(0xffffffffu, c0), b1 = __ballot_sync(0xffffffffu, c1);
+                int pos = sp + __popc(b0 & lt) + __popc(b1 & lt);
+                if (c0) { ws.stk_first[pos] = f0 | ((unsigned)(np0 - 1) << 29); ws.stk_mask[pos] = om.x; ++pos; }
+                if (c1) { ws.stk_first[pos] = f1 | ((unsigned)(np1 - 1) << 29); ws.stk_mask[pos] = om.y; }
+                sp += __popc(b0) + __popc(b1);
+            } else {
+                // rare: a bucket of > 16 bodies sharing one finest-level cell is pushed in chunks
+                const int e0 = c0 ? (np0 + TRAV_CHUNK_PAIRS - 1) / TRAV_CHUNK_PAIRS : 0;
+                const int e1 = c1 ? (np1 + TRAV_CHUNK_PAIRS - 1) / TRAV_CHUNK_PAIRS : 0;
+                int inc2 = e0 + e1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, inc2, o);
+                    if ((int)lane >= o) inc2 += u;
+                }
+                const int total = __shfl_sync(0xffffffffu, inc2, 31);
+                if (sp + total > TRAV_CAP) {   // never drop silently
+                    if (lane == 0) atomicOr(error, (unsigned)ERR_STACK_OVERFLOW);
+                    sp = 0;
+                } else {
+                    int pos = sp + inc2 - (e0 + e1);
+                    for (int q = 0; q < e0; ++q, ++pos) {
+                        const int r = min(np0 - TRAV_CHUNK_PAIRS * q, TRAV_CHUNK_PAIRS);
+                        ws.stk_first[pos] = (f0 + (unsigned)(TRAV_CHUNK_PAIRS * q)) | ((unsigned)(r - 1) << 29);
+                        ws.stk_mask[pos] = om.x;
                     }
+                    for (int q = 0; q < e1; ++q, ++pos) {
+                        const int r = min(np1 - TRAV_CHUNK_PAIRS * q, TRAV_CHUNK_PAIRS);
+                        ws.stk_first[pos] = (f1 + (unsigned)(TRAV_CHUNK_PAIRS * q)) | ((unsigned)(r - 1) << 29);
+                        ws.stk_mask[pos] = om.y;
+                    }
+                    sp += total;
                 }
             }
+            if (COUNT) { ++w_batches; w_spmax = max(w_spmax, sp); }
             __syncwarp();
         }
-        const int cnt = evals - opens;
-        if (valid) acc[k] = make_float4(G * (ax.x + ax.y), G * (ay.x + ay.y), G * (az.x + az.y), __int_as_float(cnt));
-        unsigned c32 = valid ? (unsigned)cnt : 0u;
-        for (int o = 16; o > 0; o >>= 1) c32 += __shfl_xor_sync(0xffffffffu, c32, o);
-        wcount += c32;
+        // acc.w: exact interaction count (COUNT) or the tile's evaluated pair slots (a cost proxy)
+        if (valid) acc[k] = make_float4(G * (ax.x + ax.y), G * (ay.x + ay.y), G * (az.x + az.y), __int_as_float(COUNT ? cnt : slots));
+        if (COUNT) {
+            unsigned c32 = valid ? (unsigned)cnt : 0u, l32 = (unsigned)lanepairs;
+            for (int o = 16; o > 0; o >>= 1) {
+                c32 += __shfl_xor_sync(0xffffffffu, c32, o);
+                l32 += __shfl_xor_sync(0xffffffffu, l32, o);
+            }
+            w_inter += c32;
+            w_lanepairs += l32;
+            w_slots += (unsigned)slots;
+        }
     }
-    if (COUNT && lane == 0 && wcount) atomicAdd(interactions, wcount);
+    if (COUNT && lane == 0) {
+        if (w_inter) atomicAdd(&counters[0], w_inter);
+        atomicAdd(&counters[1], w_slots);
+        atomicAdd(&counters[2], w_lanepairs);
+        atomicAdd(&counters[3], w_batches);
+        atomicMax(&counters[4], (unsigned long long)w_spmax);
+    }
 }
 
 // ============================================================================ integrate
@@ -714,6 +811,7 @@ void nbody_alloc(NBodySim& s, int n)
     s.nchild = alloc_counted<int>(s, N);
     // pair records: <= (children + cells) / 2 <= 1.5 N pairs, + the root pair
     s.rec_capacity = (3 * (int64_t)N) / 2 + 16;
+    B200_REQUIRE(s.rec_capacity < (int64_t)(1u << 29), "too many bodies for the 29-bit pair index of a stack entry");
     s.recs = alloc_counted<float4>(s, 4 * (size_t)s.rec_capacity);
     s.colors = alloc_counted<float>(s, 3 * N);
     s.stage = alloc_counted<double>(s, 3 * N);
@@ -724,10 +822,12 @@ void nbody_alloc(NBodySim& s, int n)
     s.d_tile_counter = alloc_counted<unsigned>(s, 1);
     s.d_children = alloc_counted<unsigned>(s, 1);
     B200_CHECK(cudaMemset(s.d_children, 0, sizeof(unsigned)));
-    s.d_interactions = alloc_counted<unsigned long long>(s, 1);
+    s.d_interactions = alloc_counted<unsigned long long>(s, TRAV_COUNTERS);
     s.d_error = alloc_counted<unsigned>(s, 1);
     B200_CHECK(cudaMemset(s.d_error, 0, sizeof(unsigned)));
-    B200_CHECK(cudaMemset(s.d_interactions, 0, sizeof(unsigned long long)));
+    B200_CHECK(cudaMemset(s.d_interactions, 0, TRAV_COUNTERS * sizeof(unsigned long long)));
+    B200_CHECK(cudaFuncSetAttribute(traverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV_SMEM_BYTES));
+    B200_CHECK(cudaFuncSetAttribute(traverse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV_SMEM_BYTES));
     B200_CHECK(cudaMemset(s.colors, 0, 3 * N * sizeof(float)));
     s.shard_begin = 0;
     s.shard_end = n;
@@ -868,14 +968,14 @@ void nbody_traverse(NBodySim& s, int begin, int end)
         const int tile_begin = begin / 32, tile_end = div_up(end, 32);
         B200_CHECK(cudaMemsetAsync(s.d_tile_counter, 0, sizeof(unsigned), st));
         const int tiles = tile_end - tile_begin;
-        const int max_blocks = s.sm_count * 6;
+        const int max_blocks = s.sm_count * 4;
         const int blocks = min(div_up(tiles, TRAV_WARPS), max_blocks);
         const float eps2 = (float)(s.softening * s.softening);
         if (s.count_interactions)
-            traverse_kernel<true><<<blocks, TRAV_BLOCK, 0, st>>>(s.recs, s.posm, s.acc, tile_begin, tile_end, min(end, s.n),
+            traverse_kernel<true><<<blocks, TRAV_BLOCK, TRAV_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, tile_begin, tile_end, min(end, s.n),
                                                                  eps2, (float)s.G, s.d_tile_counter, s.d_interactions, s.d_error);
         else
-            traverse_kernel<false><<<blocks, TRAV_BLOCK, 0, st>>>(s.recs, s.posm, s.acc, tile_begin, tile_end, min(end, s.n),
+            traverse_kernel<false><<<blocks, TRAV_BLOCK, TRAV_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, tile_begin, tile_end, min(end, s.n),
                                                                   eps2, (float)s.G, s.d_tile_counter, s.d_interactions, s.d_error);
         ++s.launches;
         B200_CHECK(cudaGetLastError());

@@ -15,7 +15,7 @@
 //                sorted bodies, so any node's mass / centre of mass is a difference of two entries
 //   recs       octree "pair records", 64 B each = 4 x float4, holding children 2j and 2j+1 of
 //              a cell side by side for packed fp32x2 math:
-//                {x0,x1,y0,y1} {z0,z1,m0,m1} {T0,T1,first0,first1} {nchild0,nchild1,body0,body1}
+//                {x0,x1,y0,y1} {z0,z1,m0,m1} {T0,T1,-,-} {first0,first1,nchild0,nchild1}
 //              T = max(size^2/theta^2, eps^2) (leaf: eps^2); the children of a cell are
 //              CONTIGUOUS pairs, so opening a cell is one coalesced 16-byte-per-lane load.
 //   acc        (N) float4 {ax, ay, az, interaction count} in sorted order
@@ -30,8 +30,11 @@ struct __align__(16) D4 { double x, y, z, w; };
 constexpr int MORTON_LEVELS = 21;
 constexpr int TRAV_BLOCK = 256;
 constexpr int TRAV_WARPS = TRAV_BLOCK / 32;
-constexpr int TRAV_STACK = 160;      // >= 1 + 7 * 21: only cells that must be opened are pushed
-constexpr int TRAV_STAGE = 16;       // records staged per chunk (32 lanes x 16 B)
+constexpr int TRAV_BATCH = 32;       // pair slots evaluated per batch
+constexpr int TRAV_AREA = TRAV_BATCH + 2;   // entries between staging areas (bank offset of 32 B)
+constexpr int TRAV_CAP = 512;        // stack entries per warp (only cells that must be opened are pushed)
+constexpr int TRAV_DFS_MARK = 256;   // above this many entries a batch pops only the top one
+constexpr int TRAV_COUNTERS = 8;     // interactions, pair slots, lane-pairs, batches, stack high-water
 
 enum NBodyPhase { PH_KEYGEN = 0, PH_SORT, PH_GATHER, PH_BUILD, PH_EXTRACT, PH_TRAVERSE, PH_EXCHANGE, PH_INTEGRATE, PH_COUNT };
 

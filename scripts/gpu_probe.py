@@ -36,6 +36,10 @@ for k, v in st["phase_ms"].items():
 print("  total", tot, "ms  -> body-updates/s", len(pos) / (tot * 1e-3))
 ips = st["interactions"] / st["timed_steps"]
 print("interactions/body", ips / len(pos), "records", st["records"], "bounds", st["bounds"])
+if st["trav_pair_slots"]:
+    print("traversal: pair slots/body", st["trav_pair_slots"] / st["timed_steps"] / len(pos) * 32,
+          "lane utilisation", st["trav_lane_pairs"] / (32 * st["trav_pair_slots"]),
+          "pairs/batch", st["trav_pair_slots"] / st["trav_batches"], "stack max", st["trav_stack_max"])
 tr = st["phase_ms"]["traverse"] / st["timed_steps"] * 1e-3
 print("traversal TFLOP/s (20 flop/interaction)", 20 * ips / tr / 1e12)
 sim.set_profiling(False)
