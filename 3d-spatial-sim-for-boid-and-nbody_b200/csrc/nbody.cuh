@@ -84,6 +84,7 @@ struct NBodySim {
     float* colors = nullptr;                  // (N,3) f32, creation order
     void* stage = nullptr;                    // (N,3) f64-sized staging for getters
     bool tree_valid = false;                  // keys/perm/tree describe the current positions
+    bool trav_transposed = false;             // experimental 8-body transposed walk instead of the 32-body batched walk
     bool count_interactions = false;          // exact per-body interaction counts in the traversal (slower)
 
     // multi-GPU: this rank traverses sorted bodies [shard_begin, shard_end) (multiples of 32)
