@@ -249,28 +249,33 @@ __device__ __forceinline__ D4 segment_sum(const D4* __restrict__ ploc, const D4*
 // reference's octree with single-child chains collapsed to their deepest cell, whose size is
 // the one that decides the reference's MAC (all chain cells share mass and COM).
 // Pass 1 walks the <= 7 same-level binary descendants of every head once, stores the <= 8
-// octree children it finds (kids[8 i .. 8 i + 7], in key = octant order) and allocates the
-// cell's pair block; pass 2 reads the list back and writes whole 64-byte pair records.
+// octree children it finds (kids[8 i .. 8 i + 7], in key = octant order), allocates the cell's
+// pair block and packs what a parent needs to know about the cell into ONE 16-byte word
+// meta[i] = {range lo, range hi, first pair, children << 5 | level}; pass 2 reads the list back
+// and writes whole 64-byte pair records (one meta sector + two prefix-sum sectors per child cell).
 // Cells at the finest level (bodies sharing all 63 key bits) are buckets: their children are the
 // leaves of their range, any number of them, and are written by a plain loop.
 constexpr int KIDS = 8;
 
 __global__ void __launch_bounds__(256) count_children_kernel(int n, const int* __restrict__ childL, const int* __restrict__ childR,
                                                              const int* __restrict__ parent, const int2* __restrict__ range,
-                                                             const signed char* __restrict__ lvl, int* __restrict__ first,
-                                                             int* __restrict__ nchild, int4* __restrict__ kids,
+                                                             const signed char* __restrict__ lvl, int4* __restrict__ meta,
+                                                             unsigned char* __restrict__ ishead, int4* __restrict__ kids,
                                                              unsigned* alloc, unsigned capacity, unsigned* error,
                                                              unsigned* children_total)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int cnt = 0;
+    int Li = 0;
+    int2 rg = make_int2(0, 0);
+    bool head = false;
     if (i < n - 1) {
-        const int Li = lvl[i];
+        Li = lvl[i];
         const int par = parent[i];
-        const bool head = par < 0 || lvl[par] != Li;
+        head = par < 0 || lvl[par] != Li;
         if (head) {
+            rg = range[i];
             if (Li >= MORTON_LEVELS) {
-                const int2 rg = range[i];
                 cnt = rg.y - rg.x + 1;
             } else {
                 int kid[KIDS];
@@ -327,10 +332,11 @@ __global__ void __launch_bounds__(256) count_children_kernel(int n, const int* _
         s_base = base;
     }
     __syncthreads();
-    if (i >= n - 1) return;
-    if (cnt == 0 || s_base == 0xffffffffu) { nchild[i] = 0; first[i] = -1; return; }
-    nchild[i] = cnt;
-    first[i] = (int)(s_base + wsum[warp] + inc - npair);
+    if (i < n - 1) ishead[i] = head ? 1 : 0;
+    // one 16-byte record per octree cell: everything write_records needs about a child cell
+    if (!head) return;
+    if (s_base == 0xffffffffu) cnt = 0;
+    meta[i] = make_int4(rg.x, rg.y, cnt ? (int)(s_base + wsum[warp] + inc - npair) : -1, (cnt << 5) | Li);
 }
 
 // Pair records: children 2j and 2j+1 of a cell share one 64-byte record laid out for packed
@@ -369,12 +375,9 @@ __device__ __forceinline__ ChildRec cell_child(const D4& S, int level, double bo
 }
 
 struct TreeView {
-    const int2* __restrict__ range;
+    const int4* __restrict__ meta;
     const D4* __restrict__ ploc;
     const D4* __restrict__ bex;
-    const signed char* __restrict__ lvl;
-    const int* __restrict__ first;
-    const int* __restrict__ nchild;
     const float4* __restrict__ posm;
 };
 
@@ -385,8 +388,8 @@ __device__ __forceinline__ ChildRec load_child(int c, const TreeView& tv, double
         const float4 b = tv.posm[k];
         return ChildRec{b.x, b.y, b.z, b.w, eps2, 0, 0, k};
     }
-    const int2 rg = tv.range[c];
-    return cell_child(segment_sum(tv.ploc, tv.bex, rg.x, rg.y), tv.lvl[c], bounds, theta, eps2, tv.first[c], tv.nchild[c]);
+    const int4 m = __ldg(&tv.meta[c]);
+    return cell_child(segment_sum(tv.ploc, tv.bex, m.x, m.y), m.w & 31, bounds, theta, eps2, m.z, m.w >> 5);
 }
 
 __device__ __forceinline__ void store_pair(float4* __restrict__ recs, int64_t pair, const ChildRec& a, const ChildRec& b)
@@ -398,40 +401,65 @@ __device__ __forceinline__ void store_pair(float4* __restrict__ recs, int64_t pa
     q[3] = make_float4(__int_as_float(a.first), __int_as_float(b.first), __int_as_float(a.nchild), __int_as_float(b.nchild));
 }
 
-__global__ void __launch_bounds__(256) write_records_kernel(int n, TreeView tv, const int4* __restrict__ kids,
+// Eight lanes per octree cell, one per child: all of a cell's children are fetched at once (meta ->
+// two prefix-sum entries, or the leaf's float4), neighbouring lanes swap their results and the even
+// lane writes the 64-byte pair record.  A warp covers 32 consecutive binary nodes and serves its
+// cells four at a time.
+__device__ __forceinline__ ChildRec shfl_down_child(unsigned mask, const ChildRec& r)
+{
+    ChildRec o;
+    o.x = __shfl_down_sync(mask, r.x, 1); o.y = __shfl_down_sync(mask, r.y, 1); o.z = __shfl_down_sync(mask, r.z, 1);
+    o.m = __shfl_down_sync(mask, r.m, 1); o.T = __shfl_down_sync(mask, r.T, 1);
+    o.first = __shfl_down_sync(mask, r.first, 1); o.nchild = __shfl_down_sync(mask, r.nchild, 1);
+    o.body = -1;
+    return o;
+}
+
+__global__ void __launch_bounds__(256) write_records_kernel(int n, TreeView tv, const unsigned char* __restrict__ ishead,
+                                                            const int* __restrict__ kids,
                                                             const double* __restrict__ bounds_p, double theta, float eps2,
                                                             float4* __restrict__ recs)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    const int nc = tv.nchild[i];
-    if (nc == 0) return;
-    const double bounds = *bounds_p;
-    const int Li = tv.lvl[i];
-    const int64_t base = tv.first[i];
-    if (i == 0)   // node 0 is the root; pair 0 = {root cell, dummy}
-        store_pair(recs, 0, cell_child(segment_sum(tv.ploc, tv.bex, 0, n - 1), Li, bounds, theta, eps2, (int)base, nc),
-                   dummy_child());
-    if (Li >= MORTON_LEVELS) {   // bucket: the leaves of the range
-        const int k0 = tv.range[i].x;
-        for (int c = 0; c < nc; c += 2) {
-            const ChildRec a = load_child(~(k0 + c), tv, bounds, theta, eps2);
-            const ChildRec b = (c + 1 < nc) ? load_child(~(k0 + c + 1), tv, bounds, theta, eps2)
-                                            : dummy_child();
-            store_pair(recs, base + (c >> 1), a, b);
-        }
-        return;
+    const unsigned lane = lane_id();
+    const int w0 = (int)((blockIdx.x * blockDim.x + threadIdx.x) & ~31u);
+    const int i = w0 + (int)lane;
+    int4 mi = make_int4(0, 0, 0, 0);
+    bool h = false;
+    if (i < n - 1 && ishead[i]) {
+        mi = __ldg(&tv.meta[i]);
+        h = (mi.w >> 5) != 0;
     }
-    const int4 k0 = kids[2 * (int64_t)i], k1 = kids[2 * (int64_t)i + 1];
-    const int kid[KIDS] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-#pragma unroll
-    for (int c = 0; c < KIDS; c += 2) {
-        if (c < nc) {
-            const ChildRec a = load_child(kid[c], tv, bounds, theta, eps2);
-            const ChildRec b = (c + 1 < nc) ? load_child(kid[c + 1], tv, bounds, theta, eps2)
-                                            : dummy_child();
-            store_pair(recs, base + (c >> 1), a, b);
+    unsigned hm = __ballot_sync(0xffffffffu, h);
+    if (!hm) return;
+    const double bounds = *bounds_p;
+    const int sub = (int)(lane >> 3), c = (int)(lane & 7u);
+    const unsigned gmask = 0xffu << (8 * sub);
+    while (hm) {
+        const unsigned src = __fns(hm, 0, sub + 1);   // lane of the sub-th remaining cell, or 0xffffffff
+        const bool have = src != 0xffffffffu;
+        const int sl = have ? (int)src : 0;
+        const int4 m = make_int4(__shfl_sync(0xffffffffu, mi.x, sl), __shfl_sync(0xffffffffu, mi.y, sl),
+                                 __shfl_sync(0xffffffffu, mi.z, sl), __shfl_sync(0xffffffffu, mi.w, sl));
+        if (have) {
+            const int node = w0 + sl;
+            const int nc = m.w >> 5, Li = m.w & 31;
+            const int64_t base = m.z;
+            const bool bucket = Li >= MORTON_LEVELS;   // cell at the finest level: its children are the leaves of its range
+            if (node == 0 && c == 0)   // node 0 is the root; pair 0 = {root cell, dummy}
+                store_pair(recs, 0, cell_child(segment_sum(tv.ploc, tv.bex, 0, n - 1), Li, bounds, theta, eps2, (int)base, nc),
+                           dummy_child());
+            for (int c0 = 0; c0 < nc; c0 += 8) {
+                const int cc = c0 + c;
+                ChildRec rec = dummy_child();
+                if (cc < nc) {
+                    const int kid = bucket ? ~(m.x + cc) : __ldg(&kids[8 * (int64_t)node + cc]);
+                    rec = load_child(kid, tv, bounds, theta, eps2);
+                }
+                const ChildRec nxt = shfl_down_child(gmask, rec);
+                if ((cc & 1) == 0 && cc < nc) store_pair(recs, base + (cc >> 1), rec, nxt);
+            }
         }
+        hm &= hm - 1; hm &= hm - 1; hm &= hm - 1; hm &= hm - 1;   // (x & (x-1) of 0 stays 0)
     }
 }
 
@@ -1068,8 +1096,9 @@ void nbody_alloc(NBodySim& s, int n)
     s.bex = alloc_counted<D4>(s, N / PFX_BLOCK + 2);
     s.lvl = alloc_counted<signed char>(s, N);
     s.kids = alloc_counted<int4>(s, 2 * N);
-    s.first = alloc_counted<int>(s, N);
-    s.nchild = alloc_counted<int>(s, N);
+    s.meta = alloc_counted<int4>(s, N);
+    s.ishead = alloc_counted<unsigned char>(s, N);
+    B200_REQUIRE(N < ((size_t)1 << 26), "too many bodies for the packed child count of a cell");
     // pair records: <= (children + cells) / 2 <= 1.5 N pairs, + the root pair
     s.rec_capacity = (3 * (int64_t)N) / 2 + 16;
     B200_REQUIRE(s.rec_capacity < (int64_t)(1u << 29), "too many bodies for the 29-bit pair index of a stack entry");
@@ -1109,7 +1138,7 @@ void nbody_free(NBodySim& s)
     }
     s.sorter.destroy();
     cudaFree(s.posm); cudaFree(s.acc); cudaFree(s.childL); cudaFree(s.childR); cudaFree(s.parent);
-    cudaFree(s.range); cudaFree(s.ploc); cudaFree(s.bex); cudaFree(s.first); cudaFree(s.nchild);
+    cudaFree(s.range); cudaFree(s.ploc); cudaFree(s.bex); cudaFree(s.meta); cudaFree(s.ishead);
     cudaFree(s.lvl); cudaFree(s.kids);
     cudaFree(s.recs); cudaFree(s.colors); cudaFree(s.stage); cudaFree(s.d_maxabs); cudaFree(s.d_bounds);
     cudaFree(s.d_children);
@@ -1210,10 +1239,10 @@ void nbody_build_tree(NBodySim& s)
         B200_CHECK(cudaMemcpyAsync(s.d_alloc, &s.h_one, sizeof(unsigned), cudaMemcpyHostToDevice, st));   // pair 0 is the root's
         B200_CHECK(cudaMemsetAsync(s.d_children, 0, sizeof(unsigned), st));
         const int g1 = div_up(n - 1, 256);
-        count_children_kernel<<<g1, 256, 0, st>>>(n, s.childL, s.childR, s.parent, s.range, s.lvl, s.first, s.nchild, s.kids,
+        count_children_kernel<<<g1, 256, 0, st>>>(n, s.childL, s.childR, s.parent, s.range, s.lvl, s.meta, s.ishead, s.kids,
                                                   s.d_alloc, (unsigned)s.rec_capacity, s.d_error, s.d_children);
-        const TreeView tv{s.range, s.ploc, s.bex, s.lvl, s.first, s.nchild, s.posm};
-        write_records_kernel<<<g1, 256, 0, st>>>(n, tv, s.kids, s.d_bounds, s.theta, eps2f, s.recs);
+        const TreeView tv{s.meta, s.ploc, s.bex, s.posm};
+        write_records_kernel<<<g1, 256, 0, st>>>(n, tv, s.ishead, reinterpret_cast<const int*>(s.kids), s.d_bounds, s.theta, eps2f, s.recs);
         s.launches += 2;
     } else {
         single_body_record_kernel<<<1, 1, 0, st>>>(s.posm, eps2f, s.recs);

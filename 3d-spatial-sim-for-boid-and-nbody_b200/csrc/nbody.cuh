@@ -63,7 +63,8 @@ struct NBodySim {
     int *childL = nullptr, *childR = nullptr, *parent = nullptr;
     int2* range = nullptr;
     D4 *ploc = nullptr, *bex = nullptr;       // blocked fp64 prefix sums of (m x, m y, m z, m)
-    int *first = nullptr, *nchild = nullptr;
+    unsigned char* ishead = nullptr;          // binary node is an octree cell
+    int4* meta = nullptr;                     // per octree cell: {range lo, range hi, first pair, children << 5 | level}
     signed char* lvl = nullptr;               // octree level of every binary node
     int4* kids = nullptr;                     // per head: its <= 8 octree children (2 x int4)
     float4* recs = nullptr;

