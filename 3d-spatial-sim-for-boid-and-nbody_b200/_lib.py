@@ -79,6 +79,10 @@ SIGNATURES = {
     "b200_nbody_set_counting": (C.c_int, [_h, C.c_int]),
     "b200_nbody_timed_steps": (C.c_int, [_h, C.c_double, C.c_int, C.POINTER(C.c_float)]),
     "b200_nbody_launch_count": (C.c_int, [_h, C.POINTER(C.c_int64)]),
+    "b200_nbody_frame_begin": (C.c_int, [_h, C.c_double, _fp, _fp]),
+    "b200_nbody_frame_wait": (C.c_int, [_h]),
+    "b200_nbody_set_state_begin": (C.c_int, [_h, _dp, _dp]),
+    "b200_nbody_set_state_commit": (C.c_int, [_h]),
     "b200_nbody_set_stream": (C.c_int, [_h, C.c_void_p, C.c_int]),
     "b200_nbody_set_shard": (C.c_int, [_h, C.c_int64, C.c_int64]),
     "b200_nbody_step_begin": (C.c_int, [_h]),

@@ -274,6 +274,31 @@ B200_API int b200_nbody_launch_count(b200_nbody* h, int64_t* out)
     return B200_OK;
 }
 
+B200_API int b200_nbody_frame_begin(b200_nbody* h, double max_speed, float* pos_out, float* col_out)
+{
+    B200_ARG(h && ((pos_out && col_out) || h->sim.n == 0), "null argument");
+    B200_ARG(max_speed > 0.0, "max_speed must be > 0");
+    B200_TRY(b200::nbody_frame_begin(h->sim, max_speed, pos_out, col_out))
+}
+
+B200_API int b200_nbody_frame_wait(b200_nbody* h)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY(b200::nbody_frame_wait(h->sim))
+}
+
+B200_API int b200_nbody_set_state_begin(b200_nbody* h, const double* pos, const double* vel)
+{
+    B200_ARG(h && ((pos && vel) || h->sim.n == 0), "null argument");
+    B200_TRY(b200::nbody_set_state_begin(h->sim, pos, vel))
+}
+
+B200_API int b200_nbody_set_state_commit(b200_nbody* h)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY(b200::nbody_set_state_commit(h->sim))
+}
+
 B200_API int b200_nbody_set_stream(b200_nbody* h, void* cuda_stream, int external)
 {
     B200_ARG(h, "handle is null");

@@ -1128,6 +1128,8 @@ void nbody_alloc(NBodySim& s, int n)
     s.timer.init();
 }
 
+static void async_free(NBodySim& s);
+
 void nbody_free(NBodySim& s)
 {
     cudaSetDevice(s.device);
@@ -1145,6 +1147,7 @@ void nbody_free(NBodySim& s)
     cudaFree(s.d_root); cudaFree(s.d_alloc); cudaFree(s.d_tile_counter); cudaFree(s.d_interactions);
     cudaFree(s.d_error);
     s.timer.destroy();
+    async_free(s);
     if (s.own_stream) cudaStreamDestroy(s.own_stream);
     s.own_stream = nullptr;
     s.stream = nullptr;
@@ -1451,6 +1454,116 @@ void nbody_get_perm(NBodySim& s, uint32_t* out)
     if (!s.tree_valid) nbody_build_tree(s);
     B200_CHECK(cudaMemcpyAsync(out, s.id[s.cur], (size_t)s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
     B200_CHECK(cudaStreamSynchronize(s.stream));
+}
+
+// ---------------------------------------------------------------------------- asynchronous host traffic
+// The reference's frame loop reads positions and colours back every frame (tools/record.py:826-832)
+// and its getters block (gpu_backend.py:394-404).  These entry points keep PCIe busy in both
+// directions while the next step computes: the device-side staging is produced on the compute
+// stream, the copies run on their own streams, events order the hand-offs.
+static void async_init(NBodySim& s)
+{
+    if (s.up_stream) return;
+    const size_t N = (size_t)s.n;
+    B200_CHECK(cudaStreamCreateWithFlags(&s.up_stream, cudaStreamNonBlocking));
+    B200_CHECK(cudaStreamCreateWithFlags(&s.down_stream, cudaStreamNonBlocking));
+    cudaEvent_t* evs[4] = {&s.ev_frame_ready, &s.ev_frame_done, &s.ev_upload_done, &s.ev_upload_consumed};
+    for (cudaEvent_t* e : evs) B200_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    s.frame_pos = alloc_counted<float>(s, 3 * N);
+    s.frame_col = alloc_counted<float>(s, 3 * N);
+    s.up_pos = alloc_counted<double>(s, 3 * N);
+    s.up_vel = alloc_counted<double>(s, 3 * N);
+}
+
+static void async_free(NBodySim& s)
+{
+    if (!s.up_stream) return;
+    cudaStreamSynchronize(s.up_stream);
+    cudaStreamSynchronize(s.down_stream);
+    cudaFree(s.frame_pos); cudaFree(s.frame_col); cudaFree(s.up_pos); cudaFree(s.up_vel);
+    cudaEventDestroy(s.ev_frame_ready); cudaEventDestroy(s.ev_frame_done);
+    cudaEventDestroy(s.ev_upload_done); cudaEventDestroy(s.ev_upload_consumed);
+    cudaStreamDestroy(s.up_stream); cudaStreamDestroy(s.down_stream);
+    s.up_stream = s.down_stream = nullptr;
+}
+
+__global__ void __launch_bounds__(256) frame_kernel(const double* __restrict__ pos, const double* __restrict__ vel,
+                                                    const uint32_t* __restrict__ id, float* __restrict__ fpos,
+                                                    float* __restrict__ fcol, int n, double max_speed)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t o = 3 * (int64_t)k, w = 3 * (int64_t)id[k];
+    const double vx = vel[o], vy = vel[o + 1], vz = vel[o + 2];
+    float r, g, b;
+    speed_color(fmin(1.0, sqrt(vx * vx + vy * vy + vz * vz) / max_speed), r, g, b);
+    fpos[w] = (float)pos[o]; fpos[w + 1] = (float)pos[o + 1]; fpos[w + 2] = (float)pos[o + 2];
+    fcol[w] = r; fcol[w + 1] = g; fcol[w + 2] = b;
+}
+
+void nbody_frame_begin(NBodySim& s, double max_speed, float* host_pos, float* host_col)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    if (s.n == 0) return;
+    async_init(s);
+    if (s.frame_pending) B200_CHECK(cudaStreamWaitEvent(s.stream, s.ev_frame_done, 0));   // staging still being read
+    frame_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.pos[s.cur], s.vel[s.cur], s.id[s.cur], s.frame_pos, s.frame_col, s.n,
+                                                         max_speed);
+    ++s.launches;
+    B200_CHECK(cudaGetLastError());
+    B200_CHECK(cudaEventRecord(s.ev_frame_ready, s.stream));
+    B200_CHECK(cudaStreamWaitEvent(s.down_stream, s.ev_frame_ready, 0));
+    const size_t bytes = 3 * (size_t)s.n * sizeof(float);
+    B200_CHECK(cudaMemcpyAsync(host_pos, s.frame_pos, bytes, cudaMemcpyDeviceToHost, s.down_stream));
+    B200_CHECK(cudaMemcpyAsync(host_col, s.frame_col, bytes, cudaMemcpyDeviceToHost, s.down_stream));
+    B200_CHECK(cudaEventRecord(s.ev_frame_done, s.down_stream));
+    s.frame_pending = true;
+}
+
+void nbody_frame_wait(NBodySim& s)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    if (!s.frame_pending) return;
+    B200_CHECK(cudaEventSynchronize(s.ev_frame_done));
+    s.frame_pending = false;
+}
+
+void nbody_set_state_begin(NBodySim& s, const double* pos, const double* vel)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    B200_REQUIRE(!s.upload_pending, "set_state_begin: the previous upload was not committed");
+    if (s.n == 0) return;
+    async_init(s);
+    // the staging may still be read by the previous commit's copies on the compute stream
+    if (s.ev_upload_consumed) B200_CHECK(cudaStreamWaitEvent(s.up_stream, s.ev_upload_consumed, 0));
+    const size_t bytes = 3 * (size_t)s.n * sizeof(double);
+    B200_CHECK(cudaMemcpyAsync(s.up_pos, pos, bytes, cudaMemcpyHostToDevice, s.up_stream));
+    B200_CHECK(cudaMemcpyAsync(s.up_vel, vel, bytes, cudaMemcpyHostToDevice, s.up_stream));
+    B200_CHECK(cudaEventRecord(s.ev_upload_done, s.up_stream));
+    s.upload_pending = true;
+}
+
+void nbody_set_state_commit(NBodySim& s)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    B200_REQUIRE(s.upload_pending || s.n == 0, "set_state_commit without set_state_begin");
+    if (s.n == 0) return;
+    const size_t bytes = 3 * (size_t)s.n * sizeof(double);
+    const int o = s.cur ^ 1;
+    // host-side wait: once commit returns the caller may reuse its host arrays (the copy was started a
+    // step earlier, so this normally returns at once)
+    B200_CHECK(cudaEventSynchronize(s.ev_upload_done));
+    B200_CHECK(cudaMemcpyAsync(s.pos[o], s.up_pos, bytes, cudaMemcpyDeviceToDevice, s.stream));
+    B200_CHECK(cudaMemcpyAsync(s.vel[o], s.up_vel, bytes, cudaMemcpyDeviceToDevice, s.stream));
+    B200_CHECK(cudaEventRecord(s.ev_upload_consumed, s.stream));
+    scatter_mass_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.mass[s.cur], s.id[s.cur], s.mass[o], s.n);
+    iota_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.id[o], s.n);
+    s.launches += 2;
+    B200_CHECK(cudaGetLastError());
+    s.cur = o;
+    recompute_maxabs(s);
+    s.tree_valid = false;
+    s.upload_pending = false;
 }
 
 }  // namespace b200

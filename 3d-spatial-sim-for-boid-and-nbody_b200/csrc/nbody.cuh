@@ -92,6 +92,14 @@ struct NBodySim {
     int rank = 0, world = 1;
     int shard_begin = 0, shard_end = 0;
 
+    // asynchronous host traffic (frame egress / state prefetch), allocated on first use
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;
+    cudaEvent_t ev_frame_ready = nullptr, ev_frame_done = nullptr;     // device staging filled / D2H finished
+    cudaEvent_t ev_upload_done = nullptr, ev_upload_consumed = nullptr; // H2D finished / staging read by the commit
+    float *frame_pos = nullptr, *frame_col = nullptr;                  // (N,3) f32 staging, creation order
+    double *up_pos = nullptr, *up_vel = nullptr;                       // (N,3) f64 staging of a prefetched state
+    bool frame_pending = false, upload_pending = false;
+
     PhaseTimer timer;
     int64_t steps = 0;
     int64_t launches = 0;                     // kernels launched by this handle (bench: gpu_launches)
@@ -123,5 +131,11 @@ void nbody_get_colors(NBodySim& s, float* out);
 void nbody_get_accelerations(NBodySim& s, float* out);   // creation order, runs build+traverse if needed
 void nbody_get_keys(NBodySim& s, uint64_t* out);
 void nbody_get_perm(NBodySim& s, uint32_t* out);
+// frame egress: colours + creation-order fp32 positions on the compute stream, D2H on a second stream
+void nbody_frame_begin(NBodySim& s, double max_speed, float* host_pos, float* host_col);
+void nbody_frame_wait(NBodySim& s);
+// state prefetch: H2D on a third stream into staging; commit swaps it in on the compute stream
+void nbody_set_state_begin(NBodySim& s, const double* pos, const double* vel);
+void nbody_set_state_commit(NBodySim& s);
 
 }  // namespace b200

@@ -175,6 +175,34 @@ class B200BarnesHutSimulation:
         dp = C.POINTER(C.c_double)
         _lib.check(self._L.b200_nbody_set_state(self._handle(), pos.ctypes.data_as(dp), vel.ctypes.data_as(dp)))
 
+    # asynchronous frame egress / state prefetch
+    def frame_begin(self, max_speed: float, out_positions: np.ndarray, out_colors: np.ndarray):
+        """compute_colors + get_positions + get_colors without blocking: the copies into the two
+        (n,3) float32 host buffers (pinned memory for real overlap) finish by ``frame_wait()``."""
+        op = self._out(out_positions, (self.n, 3), np.float32)
+        oc = self._out(out_colors, (self.n, 3), np.float32)
+        self._frame_refs = (op, oc)   # keep the buffers alive while the copy is in flight
+        fp = C.POINTER(C.c_float)
+        _lib.check(self._L.b200_nbody_frame_begin(self._handle(), float(max_speed), op.ctypes.data_as(fp), oc.ctypes.data_as(fp)))
+
+    def frame_wait(self):
+        _lib.check(self._L.b200_nbody_frame_wait(self._handle()))
+        self._frame_refs = None
+
+    def set_state_begin(self, positions: np.ndarray, velocities: np.ndarray):
+        """Start uploading a new state (creation order, fp64) on a side stream; ``set_state_commit()``
+        makes it current.  The arrays must stay untouched until the commit."""
+        pos, vel = _as_f64(positions, (3,)), _as_f64(velocities, (3,))
+        if len(pos) != self.n or len(vel) != self.n:
+            raise ValueError("set_state_begin: n differs from the simulation's")
+        self._upload_refs = (pos, vel)
+        dp = C.POINTER(C.c_double)
+        _lib.check(self._L.b200_nbody_set_state_begin(self._handle(), pos.ctypes.data_as(dp), vel.ctypes.data_as(dp)))
+
+    def set_state_commit(self):
+        _lib.check(self._L.b200_nbody_set_state_commit(self._handle()))
+        self._upload_refs = None
+
     def set_params(self, G=None, softening=None, damping=None, theta=None):
         self.G = self.G if G is None else float(G)
         self.softening = self.softening if softening is None else float(softening)

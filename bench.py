@@ -172,6 +172,68 @@ def run_reference(args):
     return 0
 
 
+# ----------------------------------------------------------------------------- boids (BASELINE configs[3])
+BOIDS_PHASE_BYTES = {"cells": 24 + 4 + 4, "sort": 4 + 3 * 16, "gather": 4 + 72 + 72, "rules": 72 + 72}
+
+
+def _measure_boids(args, torch, peaks):
+    """1 M boids, config/boids.py defaults, U(-500,500)^3 positions (boids/flock.py:488-489), dt 1/60:
+    device-timed Flock.update at step 3 (uniform) and after 500 steps (clustered), phases, e2e
+    (update + get_state to pinned host memory), CPU oracle step on the same state."""
+    from b200sim.boids.flock import B200Flock
+    from oracle import oracle as orc
+    n, dt = 1_000_000, 1.0 / 60.0
+    f = B200Flock.random(n, seed=0)
+    pos0, vel0, col0 = f.positions.copy(), f.velocities.copy(), f.colors.copy()
+    for _ in range(3):
+        f.update(dt)
+    f.sync()
+    steps = max(args.steps, 10)
+    ms_uniform = f.timed_steps(dt, steps) / steps
+    f.reset_stats(); f.set_profiling(True)
+    for _ in range(steps):
+        f.update(dt)
+    f.sync()
+    st = f.get_stats()
+    f.set_profiling(False)
+    phases = {}
+    for k, v in st["phase_ms"].items():
+        ms = v / max(st["timed_steps"], 1)
+        e = {"ms": ms}
+        if k in BOIDS_PHASE_BYTES and ms > 0:
+            gbs = BOIDS_PHASE_BYTES[k] * n / (ms * 1e-3) / 1e9
+            e.update(algorithmic_bytes_per_boid=BOIDS_PHASE_BYTES[k], achieved_gbs=gbs, frac_of_hbm_peak=gbs / peaks["hbm_gbs"])
+        phases[k] = e
+    pairs = st["neighbor_pairs"] / max(st["timed_steps"], 1) / n
+    for _ in range(500 - 3 - 2 * steps):
+        f.update(dt)
+    f.sync()
+    ms_clustered = f.timed_steps(dt, steps) / steps
+    # e2e: update + full state to pinned host buffers (what Flock.draw reads: boids/flock.py:716-726)
+    outs = tuple(torch.empty((n, 3), dtype=torch.float64).pin_memory().numpy() for _ in range(3))
+    f.update(dt); f.get_state(out=outs)
+    t0 = time.perf_counter()
+    e2e_steps = 5
+    for _ in range(e2e_steps):
+        f.update(dt)
+        f.get_state(out=outs)
+    el = time.perf_counter() - t0
+    f.close()
+    p, v, c = pos0, vel0, col0
+    orc.boids_step(p, v, c, dt)                    # touch
+    t0 = time.perf_counter()
+    orc.boids_step(p, v, c, dt)
+    cpu_s = time.perf_counter() - t0
+    return {"workload": "boids_flock_1m", "boids": n, "dt": dt, "value": n / (ms_uniform * 1e-3), "unit": "boid-updates/s",
+            "ms_per_step": ms_uniform, "ms_per_step_after_500_steps": ms_clustered,
+            "value_after_500_steps": n / (ms_clustered * 1e-3), "neighbour_pairs_per_boid": pairs, "phases": phases,
+            "dtype": "f64", "grid": {"dim": st["grid_dim"], "cells": st["num_cells"], "key_bits": st["key_bits"]},
+            "e2e": {"value": n * e2e_steps / el, "unit": "boid-updates/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 72 * n, "what": "B200Flock.update + get_state(pos, vel, col) into pinned host buffers"},
+            "cpu_baseline": {"value": n / cpu_s, "unit": "boid-updates/s", "cores": orc.num_threads(), "kind": "port",
+                             "sample": f"one oracle Flock.update on the same 1,000,000-boid initial state; {cpu_s:.2f} s"}}
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def _make_sim(cfg, pos, vel, mass, device, rank, world, torch):
     from b200sim.nbody.gpu_backend import B200BarnesHutSimulation
@@ -252,36 +314,63 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
     out = dict(cfg=cfg, n=n, gen_s=gen_s, ms_per_step=ms_per_step, value=value, launches=launches, clocks=clocks,
                phase=phase, inter_step=inter_step, trav_ms=trav_ms, stats=st, pos=pos, vel=vel, mass=mass)
 
-    # ---- end to end through the reference-facing API with HOST buffers
+    # ---- end to end through the public API with HOST buffers, inside the timed region every step:
+    # H2D of the step's inputs (48 B/body, pinned) + step + colours + D2H of positions and colours
+    # (24 B/body, pinned).  Two variants: the reference-style blocking getters, and the asynchronous
+    # frame egress / state prefetch API (copies overlap the next step's kernels; PCIe both ways).
     if with_e2e:
         pin_pos = torch.from_numpy(pos).pin_memory()
         pin_vel = torch.from_numpy(vel).pin_memory()
         hp, hv = pin_pos.numpy(), pin_vel.numpy()
-        out_p = torch.empty((n, 3), dtype=torch.float32).pin_memory().numpy()
-        out_c = torch.empty((n, 3), dtype=torch.float32).pin_memory().numpy()
+        out_p = [torch.empty((n, 3), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+        out_c = [torch.empty((n, 3), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
         e2e_steps = max(2, min(args.steps, 5))
-        def frame():
-            sim.set_state(hp, hv)              # H2D of the step's inputs (48 B/body, pinned)
+
+        def frame_blocking():
+            sim.set_state(hp, hv)                  # H2D of the step's inputs
             sh.step(dt)
             sim.compute_colors(15.0)
-            p32 = sim.get_positions(out=out_p)  # D2H (12 B/body), as tools/record.py:828
-            c32 = sim.get_colors(out=out_c)     # D2H (12 B/body), as tools/record.py:829
-            return p32, c32
-        frame()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            frame()
-        torch.cuda.synchronize()
-        el = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(el, op=dist.ReduceOp.MAX)
-        out["e2e"] = {"value": n * e2e_steps / float(el.item()), "unit": "body-updates/s",
-                      "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 24 * n, "steps": e2e_steps,
-                      "what": "set_state(pos,vel) from pinned host memory + step + compute_colors + "
-                              "get_positions + get_colors into pinned host buffers, per step, through the ctypes C-ABI"}
+            sim.get_positions(out=out_p[0])        # D2H, as tools/record.py:828
+            sim.get_colors(out=out_c[0])           # D2H, as tools/record.py:829
+
+        def run_blocking(k):
+            for _ in range(k):
+                frame_blocking()
+
+        def run_pipelined(k):
+            sim.set_state_begin(hp, hv)            # inputs of step 0
+            for i in range(k):
+                sim.set_state_commit()
+                if i + 1 < k:
+                    sim.set_state_begin(hp, hv)    # next step's inputs upload while this step computes
+                sh.step(dt)
+                sim.frame_wait()                   # host buffers of frame i-1 are complete
+                sim.frame_begin(15.0, out_p[i & 1], out_c[i & 1])   # D2H overlaps the next step
+            sim.frame_wait()
+
+        def timed(fn):
+            fn(1)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn(e2e_steps)
+            torch.cuda.synchronize()
+            el = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(el, op=dist.ReduceOp.MAX)
+            return n * e2e_steps / float(el.item())
+
+        v_block = timed(run_blocking)
+        v_pipe = timed(run_pipelined)
+        out["e2e"] = {"value": v_pipe, "unit": "body-updates/s", "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 24 * n,
+                      "steps": e2e_steps,
+                      "what": "per step, through the ctypes C-ABI with pinned HOST buffers: set_state_begin/commit (H2D of "
+                              "positions + velocities) + step + frame_begin/wait (colours, D2H of positions + colours); the "
+                              "copies run on side streams and overlap the neighbouring steps' kernels",
+                      "blocking_value": v_block,
+                      "blocking_what": "same bytes with the reference-style blocking calls: set_state + step + compute_colors + "
+                                       "get_positions + get_colors"}
     sim.close()
     return out
 
@@ -365,6 +454,8 @@ def run_gpu(args):
                                      "frac": ach / fp32_peak if fp32_peak else None},
                         "e2e": a.get("e2e"),
                         "cpu_baseline": cpu_baseline(a["cfg"], a["pos"], a["vel"], a["mass"])}
+    if world == 1 and not args.no_also:
+        line["also_boids"] = _measure_boids(args, torch, peaks)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -83,6 +83,18 @@ int b200_nbody_sync(b200_nbody* h);
  * of tools/record.py:718-735 without rebuilding the object. */
 int b200_nbody_set_state(b200_nbody* h, const double* pos, const double* vel);
 int b200_nbody_set_params(b200_nbody* h, double G, double softening, double damping, double theta);
+/* Asynchronous frame egress (replaces the per-frame compute_colors + get_positions +
+ * get_colors of tools/record.py:826-832): colours and creation-order fp32 positions are produced on the
+ * handle's stream, the two device-to-host copies run on a second stream while later steps compute.
+ * pos_out / col_out: (n,3) fp32 host buffers (pinned for a truly asynchronous copy) that must stay
+ * untouched until frame_wait returns.  At most one frame is in flight. */
+int b200_nbody_frame_begin(b200_nbody* h, double max_speed, float* pos_out, float* col_out);
+int b200_nbody_frame_wait(b200_nbody* h);
+/* Asynchronous set_state: begin starts the host-to-device copies on a third stream into staging;
+ * commit waits for them, then makes them the current state on the handle's stream; after commit the
+ * host arrays may be reused.  Started one step ahead, the copy overlaps the previous step's kernels. */
+int b200_nbody_set_state_begin(b200_nbody* h, const double* pos, const double* vel);
+int b200_nbody_set_state_commit(b200_nbody* h);
 /* Sorted 63-bit Morton keys of the current state and the sort permutation
  * (perm[k] = creation index of the body at sorted position k). */
 int b200_nbody_get_keys(b200_nbody* h, uint64_t* out);

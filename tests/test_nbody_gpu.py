@@ -285,3 +285,39 @@ def test_full_size_properties_1m():
 def _next_bounds(sim):
     sim.get_morton_keys()          # builds the tree of the current state
     return sim.get_stats()["bounds"]
+
+
+def test_async_frame_and_state_prefetch_match_blocking_calls():
+    """frame_begin/wait == compute_colors + get_positions + get_colors; set_state_begin/commit ==
+    set_state (SURVEY.md 8f-1 frame egress)."""
+    from b200sim import presets
+    n = 20_000
+    pos, vel, mass = presets.generate("galaxy", n, 300.0, 0.1, 6)
+    mass = np.random.default_rng(1).uniform(0.5, 2.0, n)
+    a = _sim(pos, vel, mass, 0.1, 2.0, theta=0.7)
+    b = _sim(pos, vel, mass, 0.1, 2.0, theta=0.7)
+    fp = [np.empty((n, 3), np.float32) for _ in range(2)]
+    fc = [np.empty((n, 3), np.float32) for _ in range(2)]
+    for i in range(3):
+        a.step(0.05); b.step(0.05)
+        a.compute_colors(15.0)
+        b.frame_wait()
+        b.frame_begin(15.0, fp[i & 1], fc[i & 1])
+        b.step(0.05); a.step(0.05)                # the frame must be a snapshot, not the later state
+        b.frame_wait()
+        # colours/positions of the snapshot were taken before the extra step
+        # (a's getters below run after its extra step, so compare against a fresh twin instead)
+    c = _sim(pos, vel, mass, 0.1, 2.0, theta=0.7)
+    for i in range(5):
+        c.step(0.05)
+    c.compute_colors(15.0)
+    assert np.array_equal(fp[0], c.get_positions()) and np.array_equal(fc[0], c.get_colors())
+    # state prefetch
+    p2, v2 = pos[::-1].copy(), vel[::-1].copy()
+    a.set_state(p2, v2)
+    b.set_state_begin(p2, v2)
+    b.set_state_commit()
+    assert np.array_equal(a.get_positions_f64(), b.get_positions_f64())
+    assert np.array_equal(a.compute_accelerations(), b.compute_accelerations())
+    with pytest.raises(Exception):
+        b.set_state_commit()                       # nothing pending
