@@ -29,6 +29,23 @@ __global__ void __launch_bounds__(256) absmax_kernel(const double* __restrict__ 
 // 21 levels of the cube [-bounds, bounds]^3, with the reference's own fp64 arithmetic:
 // octant bit = (p >= c) (nbody/simulation.py:38-49), child centre = c +- half/2 level by
 // level (:52-60).  bounds = fma(max|coord|, 1.1, 10) (:317; numba fastmath contracts it).
+// Fast path: the descent is floor((p + bounds) / (2 bounds) * 2^21) per axis evaluated with level-by-level
+// ROUNDED centres.  Rounding moves a cell face by at most 21 ulp(bounds)/2 = 2.4e-9 finest cells and the
+// closed form below is off by < 1e-9 finest cells, so whenever the body is farther than 2^-20 finest
+// cells from every integer grid coordinate (every face of every level sits on one) both give the same
+// cell and the key is the bit interleave of the three integers.  Bodies closer than that (a few per
+// million) take the reference's exact descent.
+__device__ __forceinline__ uint64_t spread3(uint32_t v)   // bit j -> bit 3 j (21 bits)
+{
+    uint64_t x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
 __global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ pos, int n,
                                                      const unsigned long long* __restrict__ maxabs_bits,
                                                      uint64_t* __restrict__ keys, double* __restrict__ bounds_out)
@@ -38,6 +55,17 @@ __global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ 
     if (i == 0) *bounds_out = bounds;
     if (i >= n) return;
     const double px = pos[3 * (int64_t)i], py = pos[3 * (int64_t)i + 1], pz = pos[3 * (int64_t)i + 2];
+    const double inv = 1048576.0 / bounds;   // 2^21 / (2 bounds)
+    const double gx = (px + bounds) * inv, gy = (py + bounds) * inv, gz = (pz + bounds) * inv;
+    const double fx = floor(gx), fy = floor(gy), fz = floor(gz);
+    constexpr double EDGE = 1.0 / 1048576.0;
+    const double rx = gx - fx, ry = gy - fy, rz = gz - fz;
+    const bool safe = rx > EDGE && rx < 1.0 - EDGE && ry > EDGE && ry < 1.0 - EDGE && rz > EDGE && rz < 1.0 - EDGE &&
+                      fx >= 0.0 && fy >= 0.0 && fz >= 0.0 && fx < 2097152.0 && fy < 2097152.0 && fz < 2097152.0;
+    if (safe) {
+        keys[i] = spread3((uint32_t)fx) | spread3((uint32_t)fy) << 1 | spread3((uint32_t)fz) << 2;
+        return;
+    }
     double cx = 0.0, cy = 0.0, cz = 0.0, hs = bounds;
     uint64_t k = 0;
 #pragma unroll

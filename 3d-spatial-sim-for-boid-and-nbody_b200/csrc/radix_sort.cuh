@@ -83,7 +83,7 @@ static __global__ void __launch_bounds__(RADIX) scan_hist_kernel(unsigned* ghist
 
 // ---------------------------------------------------------------- one pass
 template <typename K, int ITEMS, bool IOTA>
-__global__ void __launch_bounds__(BLOCK) onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out,
+__global__ void __launch_bounds__(BLOCK, 4) onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out,
                                                          const uint32_t* __restrict__ vals_in,
                                                          uint32_t* __restrict__ vals_out, int n, int shift,
                                                          const unsigned* __restrict__ digit_start,
