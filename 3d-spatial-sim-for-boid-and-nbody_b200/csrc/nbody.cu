@@ -24,6 +24,9 @@ __global__ void __launch_bounds__(256) absmax_kernel(const double* __restrict__ 
     }
 }
 
+// MAC threshold of a cell at an octree level (defined with the records below); keygen tabulates it.
+__device__ float cell_threshold(int level, double bounds, double theta, float eps2);
+
 // ============================================================================ Morton keys
 // The key is the octant path the reference's insertion descent takes for this body through
 // 21 levels of the cube [-bounds, bounds]^3, with the reference's own fp64 arithmetic:
@@ -48,11 +51,13 @@ __device__ __forceinline__ uint64_t spread3(uint32_t v)   // bit j -> bit 3 j (2
 
 __global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ pos, int n,
                                                      const unsigned long long* __restrict__ maxabs_bits,
-                                                     uint64_t* __restrict__ keys, double* __restrict__ bounds_out)
+                                                     uint64_t* __restrict__ keys, double* __restrict__ bounds_out,
+                                                     float* __restrict__ ttab, double theta, float eps2)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const double bounds = __fma_rn(__longlong_as_double((long long)*maxabs_bits), 1.1, 10.0);
     if (i == 0) *bounds_out = bounds;
+    if (blockIdx.x == 0 && threadIdx.x <= MORTON_LEVELS) ttab[threadIdx.x] = cell_threshold((int)threadIdx.x, bounds, theta, eps2);
     if (i >= n) return;
     const double px = pos[3 * (int64_t)i], py = pos[3 * (int64_t)i + 1], pz = pos[3 * (int64_t)i + 2];
     const double inv = 1048576.0 / bounds;   // 2^21 / (2 bounds)
@@ -84,14 +89,24 @@ __global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ 
 // ============================================================================ gather
 // Physically reorder the master state into the new Morton order (nearly the identity after
 // the first step, so the reads stay close to coalesced) and emit the float4 view.
-__global__ void __launch_bounds__(256) gather_kernel(const uint32_t* __restrict__ perm,
-                                                     const double* __restrict__ pos_in, const double* __restrict__ vel_in,
-                                                     const double* __restrict__ mass_in, const uint32_t* __restrict__ id_in,
-                                                     double* __restrict__ pos_out, double* __restrict__ vel_out,
-                                                     double* __restrict__ mass_out, uint32_t* __restrict__ id_out,
-                                                     float4* __restrict__ posm, int n)
+struct GatherArgs {
+    const uint32_t* __restrict__ perm;
+    const double* __restrict__ pos_in; const double* __restrict__ vel_in; const double* __restrict__ mass_in;
+    const uint32_t* __restrict__ id_in;
+    double* __restrict__ pos_out; double* __restrict__ vel_out; double* __restrict__ mass_out;
+    uint32_t* __restrict__ id_out;
+    float4* __restrict__ posm;
+};
+
+__device__ __forceinline__ void gather_block(int block, const GatherArgs& a, int n)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t* __restrict__ perm = a.perm;
+    const double* __restrict__ pos_in = a.pos_in; const double* __restrict__ vel_in = a.vel_in;
+    const double* __restrict__ mass_in = a.mass_in; const uint32_t* __restrict__ id_in = a.id_in;
+    double* __restrict__ pos_out = a.pos_out; double* __restrict__ vel_out = a.vel_out;
+    double* __restrict__ mass_out = a.mass_out; uint32_t* __restrict__ id_out = a.id_out;
+    float4* __restrict__ posm = a.posm;
+    const int k = block * 256 + (int)threadIdx.x;
     if (k >= n) return;
     const int64_t j = perm[k];
     const double x = pos_in[3 * j], y = pos_in[3 * j + 1], z = pos_in[3 * j + 2];
@@ -138,11 +153,20 @@ __device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, uint64_t
 // split by binary search on delta -- independent threads, no atomics, no fences.  Node i covers
 // the sorted bodies [range.x, range.y] (i is one of the two ends); children are internal nodes
 // (>= 0) or leaves (~k).  Node 0 is the root.  lvl = octree level of the node's smallest cell.
-__global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict__ keys, int n, int* __restrict__ childL,
-                                                     int* __restrict__ childR, int* __restrict__ parent,
-                                                     int2* __restrict__ range, signed char* __restrict__ lvl)
+struct KarrasArgs {
+    const uint64_t* __restrict__ keys;
+    int* __restrict__ childL; int* __restrict__ childR; int* __restrict__ parent;
+    int2* __restrict__ range;
+    signed char* __restrict__ lvl;
+};
+
+__device__ __forceinline__ void karras_block(int block, const KarrasArgs& a, int n)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t* __restrict__ keys = a.keys;
+    int* __restrict__ childL = a.childL; int* __restrict__ childR = a.childR; int* __restrict__ parent = a.parent;
+    int2* __restrict__ range = a.range;
+    signed char* __restrict__ lvl = a.lvl;
+    const int i = block * 256 + (int)threadIdx.x;
     if (i >= n - 1) return;
     const uint64_t ki = keys[i];
     const int dr = delta(keys, ki, i, (int64_t)i + 1, n), dl = delta(keys, ki, i, (int64_t)i - 1, n);
@@ -171,6 +195,16 @@ __global__ void __launch_bounds__(256) karras_kernel(const uint64_t* __restrict_
     if (i == 0) parent[0] = -1;
     range[i] = make_int2(lo, hi);
     lvl[i] = (signed char)level_of(dnode);
+}
+
+// The physical reorder (HBM-bound, 5 % issue utilisation) and the radix-tree topology (issue-bound,
+// 10 % DRAM utilisation) only depend on the sort, not on each other: one launch interleaves their
+// CTAs (even blocks gather, odd blocks build topology) so both run on every SM at the same time.
+__global__ void __launch_bounds__(256) gather_karras_kernel(GatherArgs g, KarrasArgs k, int n)
+{
+    const int block = (int)(blockIdx.x >> 1);
+    if (blockIdx.x & 1u) karras_block(block, k, n);
+    else gather_block(block, g, n);
 }
 
 // Mass sums of every node = differences of a prefix sum over the sorted bodies of
@@ -285,14 +319,27 @@ __device__ __forceinline__ D4 segment_sum(const D4* __restrict__ ploc, const D4*
 // leaves of their range, any number of them, and are written by a plain loop.
 constexpr int KIDS = 8;
 
-__global__ void __launch_bounds__(256) count_children_kernel(int n, const int* __restrict__ childL, const int* __restrict__ childR,
-                                                             const int* __restrict__ parent, const int2* __restrict__ range,
-                                                             const signed char* __restrict__ lvl, int4* __restrict__ meta,
-                                                             unsigned char* __restrict__ ishead, int4* __restrict__ kids,
-                                                             unsigned* alloc, unsigned capacity, unsigned* error,
-                                                             unsigned* children_total)
+struct ChildrenArgs {
+    const int* __restrict__ childL; const int* __restrict__ childR; const int* __restrict__ parent;
+    const int2* __restrict__ range;
+    const signed char* __restrict__ lvl;
+    int4* __restrict__ meta;
+    unsigned char* __restrict__ ishead;
+    int4* __restrict__ kids;
+    unsigned* alloc; unsigned capacity; unsigned* error; unsigned* children_total;
+};
+
+__device__ __forceinline__ void count_children_block(int block, int n, const ChildrenArgs& a)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int* __restrict__ childL = a.childL; const int* __restrict__ childR = a.childR; const int* __restrict__ parent = a.parent;
+    const int2* __restrict__ range = a.range;
+    const signed char* __restrict__ lvl = a.lvl;
+    int4* __restrict__ meta = a.meta;
+    unsigned char* __restrict__ ishead = a.ishead;
+    int4* __restrict__ kids = a.kids;
+    unsigned* alloc = a.alloc; const unsigned capacity = a.capacity; unsigned* error = a.error;
+    unsigned* children_total = a.children_total;
+    const int i = block * 256 + (int)threadIdx.x;
     int cnt = 0;
     int Li = 0;
     int2 rg = make_int2(0, 0);
@@ -367,6 +414,11 @@ __global__ void __launch_bounds__(256) count_children_kernel(int n, const int* _
     meta[i] = make_int4(rg.x, rg.y, cnt ? (int)(s_base + wsum[warp] + inc - npair) : -1, (cnt << 5) | Li);
 }
 
+__global__ void __launch_bounds__(256) count_children_kernel(int n, ChildrenArgs ca)
+{
+    count_children_block((int)blockIdx.x, n, ca);
+}
+
 // Pair records: children 2j and 2j+1 of a cell share one 64-byte record laid out for packed
 // fp32x2 math in the traversal (component c = child & 1):
 //   q0 = {x0, x1, y0, y1}   q1 = {z0, z1, m0, m1}   q2 = {T0, T1, -, -}
@@ -385,7 +437,7 @@ __device__ __forceinline__ ChildRec dummy_child()
     return ChildRec{REC_DUMMY_X, 0.f, 0.f, 0.f, 0.f, 0, 0, -1};
 }
 
-__device__ __forceinline__ float cell_threshold(int level, double bounds, double theta, float eps2)
+__device__ float cell_threshold(int level, double bounds, double theta, float eps2)
 {
     // cell size = 2*bounds / 2^level; MAC  size/d < theta  <=>  d^2 > size^2/theta^2
     const double size = ldexp(2.0 * bounds, -level);
@@ -394,12 +446,11 @@ __device__ __forceinline__ float cell_threshold(int level, double bounds, double
     return T;
 }
 
-__device__ __forceinline__ ChildRec cell_child(const D4& S, int level, double bounds, double theta, float eps2, int first,
-                                               int nchild)
+__device__ __forceinline__ ChildRec cell_child(const D4& S, float T, int first, int nchild)
 {
     const double inv = S.w > 0.0 ? 1.0 / S.w : 0.0;
     return ChildRec{(float)(S.x * inv), (float)(S.y * inv), (float)(S.z * inv), (float)S.w,
-                    cell_threshold(level, bounds, theta, eps2), first, nchild, -1};
+                    T, first, nchild, -1};
 }
 
 struct TreeView {
@@ -407,9 +458,10 @@ struct TreeView {
     const D4* __restrict__ ploc;
     const D4* __restrict__ bex;
     const float4* __restrict__ posm;
+    const float* __restrict__ ttab;   // MAC threshold per octree level (written by keygen)
 };
 
-__device__ __forceinline__ ChildRec load_child(int c, const TreeView& tv, double bounds, double theta, float eps2)
+__device__ __forceinline__ ChildRec load_child(int c, const TreeView& tv, float eps2)
 {
     if (c < 0) {
         const int k = ~c;
@@ -417,7 +469,7 @@ __device__ __forceinline__ ChildRec load_child(int c, const TreeView& tv, double
         return ChildRec{b.x, b.y, b.z, b.w, eps2, 0, 0, k};
     }
     const int4 m = __ldg(&tv.meta[c]);
-    return cell_child(segment_sum(tv.ploc, tv.bex, m.x, m.y), m.w & 31, bounds, theta, eps2, m.z, m.w >> 5);
+    return cell_child(segment_sum(tv.ploc, tv.bex, m.x, m.y), __ldg(&tv.ttab[m.w & 31]), m.z, m.w >> 5);
 }
 
 __device__ __forceinline__ void store_pair(float4* __restrict__ recs, int64_t pair, const ChildRec& a, const ChildRec& b)
@@ -443,9 +495,8 @@ __device__ __forceinline__ ChildRec shfl_down_child(unsigned mask, const ChildRe
     return o;
 }
 
-__global__ void __launch_bounds__(256) write_records_kernel(int n, TreeView tv, const unsigned char* __restrict__ ishead,
-                                                            const int* __restrict__ kids,
-                                                            const double* __restrict__ bounds_p, double theta, float eps2,
+__global__ void __launch_bounds__(256, 6) write_records_kernel(int n, TreeView tv, const unsigned char* __restrict__ ishead,
+                                                            const int* __restrict__ kids, float eps2,
                                                             float4* __restrict__ recs)
 {
     const unsigned lane = lane_id();
@@ -459,7 +510,6 @@ __global__ void __launch_bounds__(256) write_records_kernel(int n, TreeView tv, 
     }
     unsigned hm = __ballot_sync(0xffffffffu, h);
     if (!hm) return;
-    const double bounds = *bounds_p;
     const int sub = (int)(lane >> 3), c = (int)(lane & 7u);
     const unsigned gmask = 0xffu << (8 * sub);
     while (hm) {
@@ -474,14 +524,14 @@ __global__ void __launch_bounds__(256) write_records_kernel(int n, TreeView tv, 
             const int64_t base = m.z;
             const bool bucket = Li >= MORTON_LEVELS;   // cell at the finest level: its children are the leaves of its range
             if (node == 0 && c == 0)   // node 0 is the root; pair 0 = {root cell, dummy}
-                store_pair(recs, 0, cell_child(segment_sum(tv.ploc, tv.bex, 0, n - 1), Li, bounds, theta, eps2, (int)base, nc),
+                store_pair(recs, 0, cell_child(segment_sum(tv.ploc, tv.bex, 0, n - 1), __ldg(&tv.ttab[Li]), (int)base, nc),
                            dummy_child());
             for (int c0 = 0; c0 < nc; c0 += 8) {
                 const int cc = c0 + c;
                 ChildRec rec = dummy_child();
                 if (cc < nc) {
                     const int kid = bucket ? ~(m.x + cc) : __ldg(&kids[8 * (int64_t)node + cc]);
-                    rec = load_child(kid, tv, bounds, theta, eps2);
+                    rec = load_child(kid, tv, eps2);
                 }
                 const ChildRec nxt = shfl_down_child(gmask, rec);
                 if ((cc & 1) == 0 && cc < nc) store_pair(recs, base + (cc >> 1), rec, nxt);
@@ -1135,6 +1185,7 @@ void nbody_alloc(NBodySim& s, int n)
     s.stage = alloc_counted<double>(s, 3 * N);
     s.d_maxabs = alloc_counted<unsigned long long>(s, 2);
     s.d_bounds = alloc_counted<double>(s, 1);
+    s.d_ttab = alloc_counted<float>(s, 32);
     s.d_root = alloc_counted<int>(s, 1);
     s.d_alloc = alloc_counted<unsigned>(s, 1);
     s.d_tile_counter = alloc_counted<unsigned>(s, 1);
@@ -1170,7 +1221,7 @@ void nbody_free(NBodySim& s)
     cudaFree(s.posm); cudaFree(s.acc); cudaFree(s.childL); cudaFree(s.childR); cudaFree(s.parent);
     cudaFree(s.range); cudaFree(s.ploc); cudaFree(s.bex); cudaFree(s.meta); cudaFree(s.ishead);
     cudaFree(s.lvl); cudaFree(s.kids);
-    cudaFree(s.recs); cudaFree(s.colors); cudaFree(s.stage); cudaFree(s.d_maxabs); cudaFree(s.d_bounds);
+    cudaFree(s.recs); cudaFree(s.colors); cudaFree(s.stage); cudaFree(s.d_maxabs); cudaFree(s.d_bounds); cudaFree(s.d_ttab);
     cudaFree(s.d_children);
     cudaFree(s.d_root); cudaFree(s.d_alloc); cudaFree(s.d_tile_counter); cudaFree(s.d_interactions);
     cudaFree(s.d_error);
@@ -1238,7 +1289,8 @@ void nbody_build_tree(NBodySim& s)
     cudaStream_t st = s.stream;
     s.timer.begin(st);
     // ---- keys
-    keygen_kernel<<<grid, 256, 0, st>>>(s.pos[s.cur], n, s.d_maxabs + s.maxabs_slot, s.keys[0], s.d_bounds);
+    keygen_kernel<<<grid, 256, 0, st>>>(s.pos[s.cur], n, s.d_maxabs + s.maxabs_slot, s.keys[0], s.d_bounds, s.d_ttab, s.theta,
+                                        (float)(s.softening * s.softening));
     ++s.launches;
     B200_CHECK(cudaGetLastError());
     s.timer.mark(st);
@@ -1248,18 +1300,27 @@ void nbody_build_tree(NBodySim& s)
     s.timer.mark(st);
     // ---- physical reorder
     const int o = s.cur ^ 1;
-    gather_kernel<<<grid, 256, 0, st>>>(s.vals[s.sorted_slot], s.pos[s.cur], s.vel[s.cur], s.mass[s.cur], s.id[s.cur],
-                                        s.pos[o], s.vel[o], s.mass[o], s.id[o], s.posm, n);
+    {
+        const GatherArgs ga{s.vals[s.sorted_slot], s.pos[s.cur], s.vel[s.cur], s.mass[s.cur], s.id[s.cur],
+                            s.pos[o], s.vel[o], s.mass[o], s.id[o], s.posm};
+        const KarrasArgs ka{s.keys[s.sorted_slot], s.childL, s.childR, s.parent, s.range, s.lvl};
+        gather_karras_kernel<<<2 * grid, 256, 0, st>>>(ga, ka, n);   // phase "gather" = reorder + tree topology
+    }
     ++s.launches;
     B200_CHECK(cudaGetLastError());
     s.cur = o;
     s.timer.mark(st);
-    // ---- binary radix tree (Karras) + blocked prefix sums of (m x, m y, m z, m)
+    // ---- blocked prefix sums of (m x, m y, m z, m) = node mass / centre of mass; pass 1 of the cell
+    // extraction (children lists, pair-block allocation)
     if (n > 1) {
-        karras_kernel<<<div_up(n - 1, 256), 256, 0, st>>>(s.keys[s.sorted_slot], n, s.childL, s.childR, s.parent, s.range, s.lvl);
+        B200_CHECK(cudaMemcpyAsync(s.d_alloc, &s.h_one, sizeof(unsigned), cudaMemcpyHostToDevice, st));   // pair 0 is the root's
+        B200_CHECK(cudaMemsetAsync(s.d_children, 0, sizeof(unsigned), st));
         const int nb = div_up(n, PFX_BLOCK);
+        const ChildrenArgs ca{s.childL, s.childR, s.parent, s.range, s.lvl, s.meta, s.ishead, s.kids,
+                              s.d_alloc, (unsigned)s.rec_capacity, s.d_error, s.d_children};
         prefix_kernel<<<nb, 256, 0, st>>>(s.pos[s.cur], s.mass[s.cur], n, s.ploc, s.bex);
         prefix_blocks_kernel<<<1, 1024, 0, st>>>(s.bex, nb);
+        count_children_kernel<<<div_up(n - 1, 256), 256, 0, st>>>(n, ca);
         s.launches += 3;
         B200_CHECK(cudaGetLastError());
     }
@@ -1267,14 +1328,10 @@ void nbody_build_tree(NBodySim& s)
     // ---- octree records
     const float eps2f = (float)(s.softening * s.softening);
     if (n > 1) {
-        B200_CHECK(cudaMemcpyAsync(s.d_alloc, &s.h_one, sizeof(unsigned), cudaMemcpyHostToDevice, st));   // pair 0 is the root's
-        B200_CHECK(cudaMemsetAsync(s.d_children, 0, sizeof(unsigned), st));
         const int g1 = div_up(n - 1, 256);
-        count_children_kernel<<<g1, 256, 0, st>>>(n, s.childL, s.childR, s.parent, s.range, s.lvl, s.meta, s.ishead, s.kids,
-                                                  s.d_alloc, (unsigned)s.rec_capacity, s.d_error, s.d_children);
-        const TreeView tv{s.meta, s.ploc, s.bex, s.posm};
-        write_records_kernel<<<g1, 256, 0, st>>>(n, tv, s.ishead, reinterpret_cast<const int*>(s.kids), s.d_bounds, s.theta, eps2f, s.recs);
-        s.launches += 2;
+        const TreeView tv{s.meta, s.ploc, s.bex, s.posm, s.d_ttab};
+        write_records_kernel<<<g1, 256, 0, st>>>(n, tv, s.ishead, reinterpret_cast<const int*>(s.kids), eps2f, s.recs);
+        ++s.launches;
     } else {
         single_body_record_kernel<<<1, 1, 0, st>>>(s.posm, eps2f, s.recs);
         ++s.launches;

@@ -74,6 +74,7 @@ struct NBodySim {
     unsigned long long* d_maxabs = nullptr;   // [2] bit patterns of max |coord|
     int maxabs_slot = 0;
     double* d_bounds = nullptr;
+    float* d_ttab = nullptr;                  // MAC threshold per octree level of the current tree
     int* d_root = nullptr;
     unsigned* d_alloc = nullptr;              // pair-record allocator
     unsigned* d_children = nullptr;           // octree children (cells + leaves) of the last tree
