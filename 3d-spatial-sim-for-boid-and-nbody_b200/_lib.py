@@ -85,6 +85,9 @@ SIGNATURES = {
     "b200_nbody_set_state_commit": (C.c_int, [_h]),
     "b200_nbody_set_stream": (C.c_int, [_h, C.c_void_p, C.c_int]),
     "b200_nbody_set_shard": (C.c_int, [_h, C.c_int64, C.c_int64]),
+    "b200_nbody_sharded_sort_setup": (C.c_int, [_h, C.c_int64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "b200_nbody_sort_local": (C.c_int, [_h, C.c_int]),
+    "b200_nbody_step_begin_sorted": (C.c_int, [_h]),
     "b200_nbody_step_begin": (C.c_int, [_h]),
     "b200_nbody_step_end": (C.c_int, [_h, C.c_double]),
     "b200_nbody_acc_buffer": (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),

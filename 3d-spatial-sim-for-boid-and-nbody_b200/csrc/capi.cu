@@ -319,6 +319,29 @@ B200_API int b200_nbody_set_shard(b200_nbody* h, int64_t begin, int64_t end)
     return B200_OK;
 }
 
+B200_API int b200_nbody_sharded_sort_setup(b200_nbody* h, int64_t slice, int world, void** keys_device_ptr, void** vals_device_ptr)
+{
+    B200_ARG(h && keys_device_ptr && vals_device_ptr, "null argument");
+    B200_ARG(slice > 0 && slice < ((int64_t)1 << 31) && world > 0 && world <= 64, "bad slice / world");
+    B200_TRY({
+        b200::nbody_ms_setup(h->sim, (int)slice, world);
+        *keys_device_ptr = h->sim.ms_keys;
+        *vals_device_ptr = h->sim.ms_vals;
+    })
+}
+
+B200_API int b200_nbody_sort_local(b200_nbody* h, int rank)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY(b200::nbody_ms_sort_local(h->sim, rank))
+}
+
+B200_API int b200_nbody_step_begin_sorted(b200_nbody* h)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY(b200::nbody_step_begin_sorted(h->sim))
+}
+
 B200_API int b200_nbody_step_begin(b200_nbody* h)
 {
     B200_ARG(h, "handle is null");

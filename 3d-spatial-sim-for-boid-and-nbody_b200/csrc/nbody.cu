@@ -49,14 +49,16 @@ __device__ __forceinline__ uint64_t spread3(uint32_t v)   // bit j -> bit 3 j (2
     return x;
 }
 
-__global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ pos, int n,
+// Keys of the bodies at current positions [first, n) are written to keys[0 .. n - first).
+__global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ pos, int first, int n,
                                                      const unsigned long long* __restrict__ maxabs_bits,
                                                      uint64_t* __restrict__ keys, double* __restrict__ bounds_out,
                                                      float* __restrict__ ttab, double theta, float eps2)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = first + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    keys -= first;
     const double bounds = __fma_rn(__longlong_as_double((long long)*maxabs_bits), 1.1, 10.0);
-    if (i == 0) *bounds_out = bounds;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *bounds_out = bounds;
     if (blockIdx.x == 0 && threadIdx.x <= MORTON_LEVELS) ttab[threadIdx.x] = cell_threshold((int)threadIdx.x, bounds, theta, eps2);
     if (i >= n) return;
     const double px = pos[3 * (int64_t)i], py = pos[3 * (int64_t)i + 1], pz = pos[3 * (int64_t)i + 2];
@@ -1218,6 +1220,7 @@ void nbody_free(NBodySim& s)
         cudaFree(s.keys[b]); cudaFree(s.vals[b]);
     }
     s.sorter.destroy();
+    if (s.ms_keys) { cudaFree(s.ms_keys); cudaFree(s.ms_vals); s.ms_keys = nullptr; s.ms_vals = nullptr; }
     cudaFree(s.posm); cudaFree(s.acc); cudaFree(s.childL); cudaFree(s.childR); cudaFree(s.parent);
     cudaFree(s.range); cudaFree(s.ploc); cudaFree(s.bex); cudaFree(s.meta); cudaFree(s.ishead);
     cudaFree(s.lvl); cudaFree(s.kids);
@@ -1280,6 +1283,8 @@ void nbody_upload_state(NBodySim& s, const double* pos, const double* vel)
     B200_CHECK(cudaStreamSynchronize(s.stream));
 }
 
+static void build_after_sort(NBodySim& s);
+
 void nbody_build_tree(NBodySim& s)
 {
     B200_CHECK(cudaSetDevice(s.device));
@@ -1289,7 +1294,7 @@ void nbody_build_tree(NBodySim& s)
     cudaStream_t st = s.stream;
     s.timer.begin(st);
     // ---- keys
-    keygen_kernel<<<grid, 256, 0, st>>>(s.pos[s.cur], n, s.d_maxabs + s.maxabs_slot, s.keys[0], s.d_bounds, s.d_ttab, s.theta,
+    keygen_kernel<<<grid, 256, 0, st>>>(s.pos[s.cur], 0, n, s.d_maxabs + s.maxabs_slot, s.keys[0], s.d_bounds, s.d_ttab, s.theta,
                                         (float)(s.softening * s.softening));
     ++s.launches;
     B200_CHECK(cudaGetLastError());
@@ -1298,6 +1303,129 @@ void nbody_build_tree(NBodySim& s)
     s.sorted_slot = s.sorter.sort(s.keys, s.vals, 0, n, 0, 64, /*iota=*/true, st, s.sm_count);
     s.launches += s.sorter.last_launches;
     s.timer.mark(st);
+    build_after_sort(s);
+}
+
+// ---------------------------------------------------------------------------- sharded sort (multi-GPU)
+// Every rank holds the full state in last step's Morton order.  Rank r generates keys for and sorts only
+// the bodies at current positions [r S, (r+1) S) (S = slice); the sorted slices are all-gathered by the
+// host plumbing (12 B/body) and merged here by counting: the global rank of an element of run r is its
+// local rank + the number of elements of every earlier run that are <= it + of every later run that
+// are < it -- the result of a stable sort of the whole array, bit-identical on every rank.  Because the
+// runs were Morton ranges one step ago they barely overlap, and the counts are found by galloping from
+// the end (earlier runs) or the beginning (later runs) of the other run: O(log migrants) per run.
+__device__ __forceinline__ int count_le_from_end(const uint64_t* __restrict__ run, int len, uint64_t k)
+{   // number of elements <= k in a sorted run, expected to be close to len
+    if (len == 0 || run[len - 1] <= k) return len;
+    int hi = len - 1;          // run[hi] > k
+    int step = 1;
+    int lo = hi - step;
+    while (lo >= 0 && run[lo] > k) { hi = lo; step <<= 1; lo = hi - step; }
+    if (lo < 0) lo = -1;       // run[lo] <= k (or lo = -1), run[hi] > k
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (run[mid] <= k) lo = mid; else hi = mid;
+    }
+    return hi;
+}
+
+__device__ __forceinline__ int count_lt_from_begin(const uint64_t* __restrict__ run, int len, uint64_t k)
+{   // number of elements < k in a sorted run, expected to be close to 0
+    if (len == 0 || run[0] >= k) return 0;
+    int lo = 0;                // run[lo] < k
+    int step = 1;
+    int hi = lo + step;
+    while (hi < len && run[hi] < k) { lo = hi; step <<= 1; hi = lo + step; }
+    if (hi > len) hi = len;    // run[hi] >= k (or hi = len), run[lo] < k
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (run[mid] < k) lo = mid; else hi = mid;
+    }
+    return hi;
+}
+
+__global__ void __launch_bounds__(256) merge_runs_kernel(const uint64_t* __restrict__ rkeys, const uint32_t* __restrict__ rvals,
+                                                         int slice, int world, int n, uint64_t* __restrict__ keys_out,
+                                                         uint32_t* __restrict__ vals_out)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into the padded exchange buffers
+    const int r = (int)(g / slice), j = (int)(g % slice);
+    if (r >= world) return;
+    const int begin = r * slice;
+    const int len = max(0, min(slice, n - begin));
+    if (j >= len) return;
+    const uint64_t k = rkeys[g];
+    int rank = j;
+    for (int q = 0; q < world; ++q) {
+        if (q == r) continue;
+        const int qb = q * slice;
+        const int ql = max(0, min(slice, n - qb));
+        rank += q < r ? count_le_from_end(rkeys + qb, ql, k) : count_lt_from_begin(rkeys + qb, ql, k);
+    }
+    keys_out[rank] = k;
+    vals_out[rank] = (uint32_t)begin + rvals[g];   // local sort position -> position in the current arrays
+}
+
+void nbody_ms_setup(NBodySim& s, int slice, int world)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    B200_REQUIRE(slice > 0 && world > 0 && (int64_t)slice * world >= s.n && slice % 32 == 0, "bad slice / world for the sharded sort");
+    if (s.ms_keys && s.ms_slice == slice && s.ms_world == world) return;
+    B200_CHECK(cudaStreamSynchronize(s.stream));
+    if (s.ms_keys) { cudaFree(s.ms_keys); cudaFree(s.ms_vals); }
+    s.ms_keys = alloc_counted<uint64_t>(s, (size_t)slice * world);
+    s.ms_vals = alloc_counted<uint32_t>(s, (size_t)slice * world);
+    s.ms_slice = slice;
+    s.ms_world = world;
+}
+
+// keygen + local radix sort of the bodies at current positions [rank*slice, (rank+1)*slice) into the
+// rank's part of the exchange buffers
+void nbody_ms_sort_local(NBodySim& s, int rank)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    B200_REQUIRE(s.ms_keys && rank >= 0 && rank < s.ms_world, "sharded sort is not set up");
+    cudaStream_t st = s.stream;
+    const int begin = min(rank * s.ms_slice, s.n);
+    const int len = max(0, min(s.ms_slice, s.n - begin));
+    s.timer.begin(st);
+    uint64_t* k2[2] = {s.ms_keys + (size_t)rank * s.ms_slice, s.keys[1] + begin};
+    uint32_t* v2[2] = {s.ms_vals + (size_t)rank * s.ms_slice, s.vals[1] + begin};
+    // (rank 0's launch also writes bounds and the threshold table; every rank runs with len >= 0, and
+    // a rank with an empty slice still needs them)
+    keygen_kernel<<<max(1, div_up(len, 256)), 256, 0, st>>>(s.pos[s.cur], begin, begin + len, s.d_maxabs + s.maxabs_slot, k2[0],
+                                                             s.d_bounds, s.d_ttab, s.theta, (float)(s.softening * s.softening));
+    ++s.launches;
+    B200_CHECK(cudaGetLastError());
+    s.timer.mark(st);
+    if (len > 0) {
+        const int slot = s.sorter.sort(k2, v2, 0, len, 0, 64, /*iota=*/true, st, s.sm_count);
+        B200_REQUIRE(slot == 0, "the sharded sort expects an even number of passes");
+        s.launches += s.sorter.last_launches;
+    }
+    s.timer.mark(st);
+}
+
+// after the host plumbing has all-gathered both exchange buffers: merge + the rest of the tree build
+void nbody_build_tree_presorted(NBodySim& s)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    B200_REQUIRE(s.ms_keys, "sharded sort is not set up");
+    if (s.n == 0) { s.tree_valid = true; return; }
+    cudaStream_t st = s.stream;
+    const int64_t total = (int64_t)s.ms_slice * s.ms_world;
+    merge_runs_kernel<<<div_up(total, 256), 256, 0, st>>>(s.ms_keys, s.ms_vals, s.ms_slice, s.ms_world, s.n, s.keys[0], s.vals[0]);
+    ++s.launches;
+    B200_CHECK(cudaGetLastError());
+    s.sorted_slot = 0;
+    build_after_sort(s);
+}
+
+static void build_after_sort(NBodySim& s)
+{
+    const int n = s.n;
+    const int grid = div_up(n, 256);
+    cudaStream_t st = s.stream;
     // ---- physical reorder
     const int o = s.cur ^ 1;
     {
@@ -1399,6 +1527,12 @@ void nbody_integrate(NBodySim& s, double dt)
 void nbody_step_begin(NBodySim& s)
 {
     nbody_build_tree(s);
+    nbody_traverse(s, s.shard_begin, s.shard_end);
+}
+
+void nbody_step_begin_sorted(NBodySim& s)
+{
+    nbody_build_tree_presorted(s);
     nbody_traverse(s, s.shard_begin, s.shard_end);
 }
 

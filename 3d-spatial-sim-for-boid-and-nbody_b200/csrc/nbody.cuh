@@ -101,6 +101,11 @@ struct NBodySim {
     double *up_pos = nullptr, *up_vel = nullptr;                       // (N,3) f64 staging of a prefetched state
     bool frame_pending = false, upload_pending = false;
 
+    // sharded sort (multi-GPU): padded exchange buffers of world * slice sorted (key, local position) pairs
+    uint64_t* ms_keys = nullptr;
+    uint32_t* ms_vals = nullptr;
+    int ms_slice = 0, ms_world = 0;
+
     PhaseTimer timer;
     int64_t steps = 0;
     int64_t launches = 0;                     // kernels launched by this handle (bench: gpu_launches)
@@ -117,11 +122,16 @@ void nbody_upload_state(NBodySim& s, const double* pos, const double* vel);
 void nbody_build_tree(NBodySim& s);
 // traversal of sorted bodies [begin, end) into s.acc
 void nbody_traverse(NBodySim& s, int begin, int end);
+// sharded sort: setup the exchange buffers; keygen + local sort of one slice; merge + rest of the tree
+void nbody_ms_setup(NBodySim& s, int slice, int world);
+void nbody_ms_sort_local(NBodySim& s, int rank);
+void nbody_build_tree_presorted(NBodySim& s);
 void nbody_integrate(NBodySim& s, double dt);
 void nbody_step(NBodySim& s, double dt);
 // split step for sharded runs: begin = tree + traversal of [shard_begin, shard_end); the caller
 // then exchanges acc slices between ranks on the same stream; end = integrate of all bodies.
 void nbody_step_begin(NBodySim& s);
+void nbody_step_begin_sorted(NBodySim& s);   // after nbody_ms_sort_local + the all-gather of the exchange buffers
 void nbody_step_end(NBodySim& s, double dt);
 double fp32_peak_tflops(int device);
 void nbody_compute_colors(NBodySim& s, double max_speed);

@@ -233,6 +233,18 @@ class B200BarnesHutSimulation:
     def set_shard(self, begin: int, end: int):
         _lib.check(self._L.b200_nbody_set_shard(self._handle(), int(begin), int(end)))
 
+    def sharded_sort_setup(self, slice_size: int, world: int):
+        """(keys pointer, vals pointer) of the padded exchange buffers of the sharded sort."""
+        k, v = C.c_void_p(), C.c_void_p()
+        _lib.check(self._L.b200_nbody_sharded_sort_setup(self._handle(), int(slice_size), int(world), C.byref(k), C.byref(v)))
+        return int(k.value), int(v.value)
+
+    def sort_local(self, rank: int):
+        _lib.check(self._L.b200_nbody_sort_local(self._handle(), int(rank)))
+
+    def step_begin_sorted(self):
+        _lib.check(self._L.b200_nbody_step_begin_sorted(self._handle()))
+
     def step_begin(self):
         _lib.check(self._L.b200_nbody_step_begin(self._handle()))
 

@@ -55,7 +55,7 @@ class ShardedSimulation:
     """Wraps a B200BarnesHutSimulation replica on this rank's GPU; same duck type
     (step / compute_colors / get_* / sync) as the single-GPU object."""
 
-    def __init__(self, sim, rank: int, world: int, group=None):
+    def __init__(self, sim, rank: int, world: int, group=None, sharded_sort: bool = True):
         import torch
         self.sim, self.rank, self.world, self.group = sim, rank, world, group
         self.n = sim.n
@@ -70,12 +70,37 @@ class ShardedSimulation:
         self.acc_all = torch.as_tensor(_DeviceArray(ptr, (self.S * world, 4)), device=dev)
         # all library work on torch's current stream: the collective is ordered with the kernels
         sim.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+        # sharded sort: every rank sorts one slice of the (Morton-ordered) state, the sorted slices are
+        # all-gathered (12 B/body) and merged by counting on every rank.  Only once the state is in Morton
+        # order (from the second step after an upload); the first step sorts everything on every rank.
+        self.sharded_sort = sharded_sort and world > 1
+        self._in_morton_order = False
+        if self.sharded_sort:
+            kp, vp = sim.sharded_sort_setup(self.S, world)
+            self.keys_all = torch.as_tensor(_DeviceArray(kp, (self.S * world, 1), "<i8"), device=dev)
+            self.vals_all = torch.as_tensor(_DeviceArray(vp, (self.S * world, 1), "<i4"), device=dev)
 
     def step(self, dt: float):
-        self.sim.step_begin()
+        if self.sharded_sort and self._in_morton_order:
+            self.sim.sort_local(self.rank)
+            all_gather_slices(self.keys_all, self.rank, self.world, self.group)
+            all_gather_slices(self.vals_all, self.rank, self.world, self.group)
+            self.sim.step_begin_sorted()
+        else:
+            self.sim.step_begin()
         if self.world > 1:
             all_gather_slices(self.acc_all, self.rank, self.world, self.group)
         self.sim.step_end(dt)
+        self._in_morton_order = True
+
+    # a new state arrives in creation order: the next step must sort everything
+    def set_state(self, positions, velocities):
+        self._in_morton_order = False
+        self.sim.set_state(positions, velocities)
+
+    def set_state_commit(self):
+        self._in_morton_order = False
+        self.sim.set_state_commit()
 
     def __getattr__(self, name):   # compute_colors, get_positions, ... are replica-local
         return getattr(self.sim, name)

@@ -329,7 +329,7 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
         e2e_steps = max(2, min(args.steps, 5))
 
         def frame_blocking():
-            sim.set_state(hp, hv)                  # H2D of the step's inputs
+            sh.set_state(hp, hv)                   # H2D of the step's inputs
             sh.step(dt)
             sim.compute_colors(15.0)
             sim.get_positions(out=out_p[0])        # D2H, as tools/record.py:828
@@ -342,7 +342,7 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
         def run_pipelined(k):
             sim.set_state_begin(hp, hv)            # inputs of step 0
             for i in range(k):
-                sim.set_state_commit()
+                sh.set_state_commit()
                 if i + 1 < k:
                     sim.set_state_begin(hp, hv)    # next step's inputs upload while this step computes
                 sh.step(dt)

@@ -122,6 +122,15 @@ int b200_nbody_set_stream(b200_nbody* h, void* cuda_stream, int external);
 int b200_nbody_set_shard(b200_nbody* h, int64_t begin, int64_t end);
 int b200_nbody_step_begin(b200_nbody* h);
 int b200_nbody_step_end(b200_nbody* h, double dt);
+/* Sharded sort (optional, valid from the second step after an upload: the state is then physically in
+ * last step's Morton order, so equal slices of it are nearly disjoint key ranges).  Rank r generates
+ * keys for and sorts only the bodies at current positions [r*slice, (r+1)*slice) into its part of two
+ * padded exchange buffers (world*slice uint64 keys, world*slice uint32 local positions); the host
+ * plumbing all-gathers both on the same stream; step_begin_sorted merges the world sorted runs by
+ * counting (bit-identical to the single-GPU stable sort) and continues like step_begin. */
+int b200_nbody_sharded_sort_setup(b200_nbody* h, int64_t slice, int world, void** keys_device_ptr, void** vals_device_ptr);
+int b200_nbody_sort_local(b200_nbody* h, int rank);
+int b200_nbody_step_begin_sorted(b200_nbody* h);
 /* Device address and capacity (in float4 entries of 16 bytes) of the sorted-order
  * accelerations buffer {ax, ay, az, interaction count}. */
 int b200_nbody_acc_buffer(b200_nbody* h, void** device_ptr, int64_t* capacity_entries);
