@@ -1311,59 +1311,68 @@ void nbody_build_tree(NBodySim& s)
 // the bodies at current positions [r S, (r+1) S) (S = slice); the sorted slices are all-gathered by the
 // host plumbing (12 B/body) and merged here by counting: the global rank of an element of run r is its
 // local rank + the number of elements of every earlier run that are <= it + of every later run that
-// are < it -- the result of a stable sort of the whole array, bit-identical on every rank.  Because the
-// runs were Morton ranges one step ago they barely overlap, and the counts are found by galloping from
-// the end (earlier runs) or the beginning (later runs) of the other run: O(log migrants) per run.
-__device__ __forceinline__ int count_le_from_end(const uint64_t* __restrict__ run, int len, uint64_t k)
-{   // number of elements <= k in a sorted run, expected to be close to len
-    if (len == 0 || run[len - 1] <= k) return len;
-    int hi = len - 1;          // run[hi] > k
-    int step = 1;
-    int lo = hi - step;
-    while (lo >= 0 && run[lo] > k) { hi = lo; step <<= 1; lo = hi - step; }
-    if (lo < 0) lo = -1;       // run[lo] <= k (or lo = -1), run[hi] > k
-    while (hi - lo > 1) {
+// are < it -- the result of a stable sort of the whole array, bit-identical on every rank.
+__device__ __forceinline__ int count_le(const uint64_t* __restrict__ run, int lo, int hi, uint64_t k)
+{   // number of elements <= k in the sorted run, known to lie in [lo, hi]
+    while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (run[mid] <= k) lo = mid; else hi = mid;
+        if (run[mid] <= k) lo = mid + 1; else hi = mid;
     }
-    return hi;
+    return lo;
+}
+__device__ __forceinline__ int count_lt(const uint64_t* __restrict__ run, int lo, int hi, uint64_t k)
+{   // number of elements < k in the sorted run, known to lie in [lo, hi]
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (run[mid] < k) lo = mid + 1; else hi = mid;
+    }
+    return lo;
 }
 
-__device__ __forceinline__ int count_lt_from_begin(const uint64_t* __restrict__ run, int len, uint64_t k)
-{   // number of elements < k in a sorted run, expected to be close to 0
-    if (len == 0 || run[0] >= k) return 0;
-    int lo = 0;                // run[lo] < k
-    int step = 1;
-    int hi = lo + step;
-    while (hi < len && run[hi] < k) { lo = hi; step <<= 1; hi = lo + step; }
-    if (hi > len) hi = len;    // run[hi] >= k (or hi = len), run[lo] < k
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (run[mid] < k) lo = mid; else hi = mid;
-    }
-    return hi;
-}
+// A CTA merges MERGE_TILE consecutive elements of one run.  The counts in every other run are monotone
+// along the tile, so one thread per other run brackets them with two full binary searches at the tile's
+// first and last key; runs that were Morton ranges one step ago barely interleave, the bracket is
+// usually empty (count constant over the tile) and otherwise a few elements wide.
+constexpr int MERGE_TILE = 4096;
+constexpr int MERGE_MAX_WORLD = 64;
 
 __global__ void __launch_bounds__(256) merge_runs_kernel(const uint64_t* __restrict__ rkeys, const uint32_t* __restrict__ rvals,
-                                                         int slice, int world, int n, uint64_t* __restrict__ keys_out,
-                                                         uint32_t* __restrict__ vals_out)
+                                                         int slice, int world, int n, int tiles_per_run,
+                                                         uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out)
 {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // index into the padded exchange buffers
-    const int r = (int)(g / slice), j = (int)(g % slice);
-    if (r >= world) return;
+    __shared__ int s_lo[MERGE_MAX_WORLD], s_hi[MERGE_MAX_WORLD];
+    const int r = (int)(blockIdx.x / tiles_per_run), tile = (int)(blockIdx.x % tiles_per_run);
     const int begin = r * slice;
     const int len = max(0, min(slice, n - begin));
-    if (j >= len) return;
-    const uint64_t k = rkeys[g];
-    int rank = j;
-    for (int q = 0; q < world; ++q) {
-        if (q == r) continue;
+    const int j0 = tile * MERGE_TILE;
+    if (j0 >= len) return;
+    const int j1 = min(j0 + MERGE_TILE, len) - 1;     // last element of the tile
+    const uint64_t* __restrict__ mine = rkeys + begin;
+    if ((int)threadIdx.x < world) {
+        const int q = (int)threadIdx.x;
         const int qb = q * slice;
         const int ql = max(0, min(slice, n - qb));
-        rank += q < r ? count_le_from_end(rkeys + qb, ql, k) : count_lt_from_begin(rkeys + qb, ql, k);
+        int lo = 0, hi = 0;
+        if (q != r) {
+            const uint64_t kf = mine[j0], kl = mine[j1];
+            if (q < r) { lo = count_le(rkeys + qb, 0, ql, kf); hi = count_le(rkeys + qb, lo, ql, kl); }
+            else { lo = count_lt(rkeys + qb, 0, ql, kf); hi = count_lt(rkeys + qb, lo, ql, kl); }
+        }
+        s_lo[q] = lo;
+        s_hi[q] = hi;
     }
-    keys_out[rank] = k;
-    vals_out[rank] = (uint32_t)begin + rvals[g];   // local sort position -> position in the current arrays
+    __syncthreads();
+    for (int j = j0 + (int)threadIdx.x; j <= j1; j += 256) {
+        const uint64_t k = mine[j];
+        int rank = j;
+        for (int q = 0; q < world; ++q) {
+            const int lo = s_lo[q], hi = s_hi[q];
+            if (lo == hi) rank += lo;
+            else rank += q < r ? count_le(rkeys + q * slice, lo, hi, k) : count_lt(rkeys + q * slice, lo, hi, k);
+        }
+        keys_out[rank] = k;
+        vals_out[rank] = (uint32_t)begin + rvals[begin + j];   // local sort position -> position in the current arrays
+    }
 }
 
 void nbody_ms_setup(NBodySim& s, int slice, int world)
@@ -1413,8 +1422,9 @@ void nbody_build_tree_presorted(NBodySim& s)
     B200_REQUIRE(s.ms_keys, "sharded sort is not set up");
     if (s.n == 0) { s.tree_valid = true; return; }
     cudaStream_t st = s.stream;
-    const int64_t total = (int64_t)s.ms_slice * s.ms_world;
-    merge_runs_kernel<<<div_up(total, 256), 256, 0, st>>>(s.ms_keys, s.ms_vals, s.ms_slice, s.ms_world, s.n, s.keys[0], s.vals[0]);
+    const int tiles_per_run = div_up(s.ms_slice, MERGE_TILE);
+    merge_runs_kernel<<<tiles_per_run * s.ms_world, 256, 0, st>>>(s.ms_keys, s.ms_vals, s.ms_slice, s.ms_world, s.n, tiles_per_run,
+                                                                  s.keys[0], s.vals[0]);
     ++s.launches;
     B200_CHECK(cudaGetLastError());
     s.sorted_slot = 0;
