@@ -83,6 +83,10 @@ SIGNATURES = {
     "b200_nbody_frame_wait": (C.c_int, [_h]),
     "b200_nbody_set_state_begin": (C.c_int, [_h, _dp, _dp]),
     "b200_nbody_set_state_commit": (C.c_int, [_h]),
+    "b200_nbody_set_state_begin_rows": (C.c_int, [_h, _dp, _dp, C.c_int64, C.c_int64]),
+    "b200_nbody_upload_staging": (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "b200_nbody_upload_wait": (C.c_int, [_h]),
+    "b200_nbody_frame_begin_rows": (C.c_int, [_h, C.c_double, _fp, _fp, C.c_int64, C.c_int64]),
     "b200_nbody_set_stream": (C.c_int, [_h, C.c_void_p, C.c_int]),
     "b200_nbody_set_shard": (C.c_int, [_h, C.c_int64, C.c_int64]),
     "b200_nbody_sharded_sort_setup": (C.c_int, [_h, C.c_int64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),

@@ -293,6 +293,39 @@ B200_API int b200_nbody_set_state_begin(b200_nbody* h, const double* pos, const 
     B200_TRY(b200::nbody_set_state_begin(h->sim, pos, vel))
 }
 
+B200_API int b200_nbody_set_state_begin_rows(b200_nbody* h, const double* pos, const double* vel, int64_t row_begin, int64_t row_end)
+{
+    B200_ARG(h && ((pos && vel) || h->sim.n == 0), "null argument");
+    B200_ARG(row_begin >= 0 && row_begin <= row_end && row_end <= h->sim.n, "rows out of range");
+    B200_TRY(b200::nbody_set_state_begin_rows(h->sim, pos, vel, (int)row_begin, (int)row_end))
+}
+
+B200_API int b200_nbody_upload_staging(b200_nbody* h, void** pos_device_ptr, void** vel_device_ptr)
+{
+    B200_ARG(h && pos_device_ptr && vel_device_ptr, "null argument");
+    B200_TRY({
+        double *p = nullptr, *v = nullptr;
+        b200::nbody_upload_staging(h->sim, &p, &v);
+        *pos_device_ptr = p;
+        *vel_device_ptr = v;
+    })
+}
+
+B200_API int b200_nbody_upload_wait(b200_nbody* h)
+{
+    B200_ARG(h, "handle is null");
+    B200_TRY(b200::nbody_upload_wait(h->sim))
+}
+
+B200_API int b200_nbody_frame_begin_rows(b200_nbody* h, double max_speed, float* pos_out, float* col_out, int64_t row_begin,
+                                         int64_t row_end)
+{
+    B200_ARG(h && ((pos_out && col_out) || h->sim.n == 0), "null argument");
+    B200_ARG(max_speed > 0.0, "max_speed must be > 0");
+    B200_ARG(row_begin >= 0 && row_begin <= row_end && row_end <= h->sim.n, "rows out of range");
+    B200_TRY(b200::nbody_frame_begin_rows(h->sim, max_speed, pos_out, col_out, (int)row_begin, (int)row_end))
+}
+
 B200_API int b200_nbody_set_state_commit(b200_nbody* h)
 {
     B200_ARG(h, "handle is null");

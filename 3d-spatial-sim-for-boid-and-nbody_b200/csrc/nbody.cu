@@ -1700,8 +1700,8 @@ static void async_init(NBodySim& s)
     for (cudaEvent_t* e : evs) B200_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     s.frame_pos = alloc_counted<float>(s, 3 * N);
     s.frame_col = alloc_counted<float>(s, 3 * N);
-    s.up_pos = alloc_counted<double>(s, 3 * N);
-    s.up_vel = alloc_counted<double>(s, 3 * N);
+    s.up_pos = alloc_counted<double>(s, 3 * (N + 64));   // + padding rows: equal all-gather slices up to 64 ranks
+    s.up_vel = alloc_counted<double>(s, 3 * (N + 64));
 }
 
 static void async_free(NBodySim& s)
@@ -1732,6 +1732,12 @@ __global__ void __launch_bounds__(256) frame_kernel(const double* __restrict__ p
 
 void nbody_frame_begin(NBodySim& s, double max_speed, float* host_pos, float* host_col)
 {
+    nbody_frame_begin_rows(s, max_speed, host_pos, host_col, 0, s.n);
+}
+
+// rows [row_begin, row_end) of the frame only (creation order): sharded frame egress, one slice per rank
+void nbody_frame_begin_rows(NBodySim& s, double max_speed, float* host_pos, float* host_col, int row_begin, int row_end)
+{
     B200_CHECK(cudaSetDevice(s.device));
     if (s.n == 0) return;
     async_init(s);
@@ -1742,9 +1748,12 @@ void nbody_frame_begin(NBodySim& s, double max_speed, float* host_pos, float* ho
     B200_CHECK(cudaGetLastError());
     B200_CHECK(cudaEventRecord(s.ev_frame_ready, s.stream));
     B200_CHECK(cudaStreamWaitEvent(s.down_stream, s.ev_frame_ready, 0));
-    const size_t bytes = 3 * (size_t)s.n * sizeof(float);
-    B200_CHECK(cudaMemcpyAsync(host_pos, s.frame_pos, bytes, cudaMemcpyDeviceToHost, s.down_stream));
-    B200_CHECK(cudaMemcpyAsync(host_col, s.frame_col, bytes, cudaMemcpyDeviceToHost, s.down_stream));
+    B200_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= s.n, "frame rows out of range");
+    const size_t off = 3 * (size_t)row_begin, bytes = 3 * (size_t)(row_end - row_begin) * sizeof(float);
+    if (bytes) {
+        B200_CHECK(cudaMemcpyAsync(host_pos + off, s.frame_pos + off, bytes, cudaMemcpyDeviceToHost, s.down_stream));
+        B200_CHECK(cudaMemcpyAsync(host_col + off, s.frame_col + off, bytes, cudaMemcpyDeviceToHost, s.down_stream));
+    }
     B200_CHECK(cudaEventRecord(s.ev_frame_done, s.down_stream));
     s.frame_pending = true;
 }
@@ -1759,15 +1768,43 @@ void nbody_frame_wait(NBodySim& s)
 
 void nbody_set_state_begin(NBodySim& s, const double* pos, const double* vel)
 {
+    nbody_set_state_begin_rows(s, pos, vel, 0, s.n);
+}
+
+void nbody_upload_staging(NBodySim& s, double** pos, double** vel)
+{
     B200_CHECK(cudaSetDevice(s.device));
+    async_init(s);
+    *pos = s.up_pos;
+    *vel = s.up_vel;
+}
+
+// the compute stream waits (on the device) for the pending upload: whatever the caller enqueues next on
+// that stream -- e.g. an all-gather of the staging slices -- sees the uploaded rows
+void nbody_upload_wait(NBodySim& s)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    B200_REQUIRE(s.upload_pending || s.n == 0, "upload_wait without set_state_begin");
+    if (s.n == 0) return;
+    B200_CHECK(cudaStreamWaitEvent(s.stream, s.ev_upload_done, 0));
+}
+
+// rows [row_begin, row_end) only: sharded upload, the caller completes the staging buffers on the
+// compute stream (upload_wait + all-gather) before set_state_commit
+void nbody_set_state_begin_rows(NBodySim& s, const double* pos, const double* vel, int row_begin, int row_end)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    B200_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= s.n, "upload rows out of range");
     B200_REQUIRE(!s.upload_pending, "set_state_begin: the previous upload was not committed");
     if (s.n == 0) return;
     async_init(s);
     // the staging may still be read by the previous commit's copies on the compute stream
     if (s.ev_upload_consumed) B200_CHECK(cudaStreamWaitEvent(s.up_stream, s.ev_upload_consumed, 0));
-    const size_t bytes = 3 * (size_t)s.n * sizeof(double);
-    B200_CHECK(cudaMemcpyAsync(s.up_pos, pos, bytes, cudaMemcpyHostToDevice, s.up_stream));
-    B200_CHECK(cudaMemcpyAsync(s.up_vel, vel, bytes, cudaMemcpyHostToDevice, s.up_stream));
+    const size_t off = 3 * (size_t)row_begin, bytes = 3 * (size_t)(row_end - row_begin) * sizeof(double);
+    if (bytes) {
+        B200_CHECK(cudaMemcpyAsync(s.up_pos + off, pos + off, bytes, cudaMemcpyHostToDevice, s.up_stream));
+        B200_CHECK(cudaMemcpyAsync(s.up_vel + off, vel + off, bytes, cudaMemcpyHostToDevice, s.up_stream));
+    }
     B200_CHECK(cudaEventRecord(s.ev_upload_done, s.up_stream));
     s.upload_pending = true;
 }

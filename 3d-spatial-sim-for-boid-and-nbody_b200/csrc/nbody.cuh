@@ -144,9 +144,13 @@ void nbody_get_keys(NBodySim& s, uint64_t* out);
 void nbody_get_perm(NBodySim& s, uint32_t* out);
 // frame egress: colours + creation-order fp32 positions on the compute stream, D2H on a second stream
 void nbody_frame_begin(NBodySim& s, double max_speed, float* host_pos, float* host_col);
+void nbody_frame_begin_rows(NBodySim& s, double max_speed, float* host_pos, float* host_col, int row_begin, int row_end);
 void nbody_frame_wait(NBodySim& s);
 // state prefetch: H2D on a third stream into staging; commit swaps it in on the compute stream
 void nbody_set_state_begin(NBodySim& s, const double* pos, const double* vel);
+void nbody_set_state_begin_rows(NBodySim& s, const double* pos, const double* vel, int row_begin, int row_end);
+void nbody_upload_staging(NBodySim& s, double** pos, double** vel);
+void nbody_upload_wait(NBodySim& s);
 void nbody_set_state_commit(NBodySim& s);
 
 }  // namespace b200

@@ -176,20 +176,24 @@ class B200BarnesHutSimulation:
         _lib.check(self._L.b200_nbody_set_state(self._handle(), pos.ctypes.data_as(dp), vel.ctypes.data_as(dp)))
 
     # asynchronous frame egress / state prefetch
-    def frame_begin(self, max_speed: float, out_positions: np.ndarray, out_colors: np.ndarray):
+    def frame_begin(self, max_speed: float, out_positions: np.ndarray, out_colors: np.ndarray, rows=None):
         """compute_colors + get_positions + get_colors without blocking: the copies into the two
         (n,3) float32 host buffers (pinned memory for real overlap) finish by ``frame_wait()``."""
         op = self._out(out_positions, (self.n, 3), np.float32)
         oc = self._out(out_colors, (self.n, 3), np.float32)
         self._frame_refs = (op, oc)   # keep the buffers alive while the copy is in flight
         fp = C.POINTER(C.c_float)
-        _lib.check(self._L.b200_nbody_frame_begin(self._handle(), float(max_speed), op.ctypes.data_as(fp), oc.ctypes.data_as(fp)))
+        if rows is None:
+            _lib.check(self._L.b200_nbody_frame_begin(self._handle(), float(max_speed), op.ctypes.data_as(fp), oc.ctypes.data_as(fp)))
+        else:   # sharded egress: only rows [begin, end) of the two buffers are filled by this replica
+            _lib.check(self._L.b200_nbody_frame_begin_rows(self._handle(), float(max_speed), op.ctypes.data_as(fp),
+                                                           oc.ctypes.data_as(fp), int(rows[0]), int(rows[1])))
 
     def frame_wait(self):
         _lib.check(self._L.b200_nbody_frame_wait(self._handle()))
         self._frame_refs = None
 
-    def set_state_begin(self, positions: np.ndarray, velocities: np.ndarray):
+    def set_state_begin(self, positions: np.ndarray, velocities: np.ndarray, rows=None):
         """Start uploading a new state (creation order, fp64) on a side stream; ``set_state_commit()``
         makes it current.  The arrays must stay untouched until the commit."""
         pos, vel = _as_f64(positions, (3,)), _as_f64(velocities, (3,))
@@ -197,7 +201,20 @@ class B200BarnesHutSimulation:
             raise ValueError("set_state_begin: n differs from the simulation's")
         self._upload_refs = (pos, vel)
         dp = C.POINTER(C.c_double)
-        _lib.check(self._L.b200_nbody_set_state_begin(self._handle(), pos.ctypes.data_as(dp), vel.ctypes.data_as(dp)))
+        if rows is None:
+            _lib.check(self._L.b200_nbody_set_state_begin(self._handle(), pos.ctypes.data_as(dp), vel.ctypes.data_as(dp)))
+        else:   # sharded upload: this replica copies rows [begin, end) only (see upload_staging / upload_wait)
+            _lib.check(self._L.b200_nbody_set_state_begin_rows(self._handle(), pos.ctypes.data_as(dp), vel.ctypes.data_as(dp),
+                                                               int(rows[0]), int(rows[1])))
+
+    def upload_staging(self):
+        """(pos pointer, vel pointer) of the (n + 64, 3) float64 device staging buffers of set_state_begin."""
+        p, v = C.c_void_p(), C.c_void_p()
+        _lib.check(self._L.b200_nbody_upload_staging(self._handle(), C.byref(p), C.byref(v)))
+        return int(p.value), int(v.value)
+
+    def upload_wait(self):
+        _lib.check(self._L.b200_nbody_upload_wait(self._handle()))
 
     def set_state_commit(self):
         _lib.check(self._L.b200_nbody_set_state_commit(self._handle()))

@@ -75,6 +75,7 @@ class ShardedSimulation:
         # order (from the second step after an upload); the first step sorts everything on every rank.
         self.sharded_sort = sharded_sort and world > 1
         self._in_morton_order = False
+        self._stage = None
         if self.sharded_sort:
             kp, vp = sim.sharded_sort_setup(self.S, world)
             self.keys_all = torch.as_tensor(_DeviceArray(kp, (self.S * world, 1), "<i8"), device=dev)
@@ -98,9 +99,31 @@ class ShardedSimulation:
         self._in_morton_order = False
         self.sim.set_state(positions, velocities)
 
+    # sharded host traffic: every rank moves 1/world of the rows over its own PCIe link; the upload is
+    # completed over NVLink (all-gather of the staging slices), the frame stays split across the ranks
+    def host_rows(self):
+        R = -(-self.n // self.world)
+        return min(self.rank * R, self.n), min((self.rank + 1) * R, self.n)
+
+    def set_state_begin(self, positions, velocities):
+        self.sim.set_state_begin(positions, velocities, rows=self.host_rows() if self.world > 1 else None)
+
     def set_state_commit(self):
         self._in_morton_order = False
+        if self.world > 1:
+            torch = self._torch
+            if self._stage is None:
+                R = -(-self.n // self.world)
+                pp, vp = self.sim.upload_staging()
+                dev = torch.device("cuda", self.sim.device)
+                self._stage = tuple(torch.as_tensor(_DeviceArray(p, (R * self.world, 3), "<f8"), device=dev) for p in (pp, vp))
+            self.sim.upload_wait()
+            for t in self._stage:
+                all_gather_slices(t, self.rank, self.world, self.group)
         self.sim.set_state_commit()
+
+    def frame_begin(self, max_speed, out_positions, out_colors):
+        self.sim.frame_begin(max_speed, out_positions, out_colors, rows=self.host_rows() if self.world > 1 else None)
 
     def __getattr__(self, name):   # compute_colors, get_positions, ... are replica-local
         return getattr(self.sim, name)

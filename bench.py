@@ -340,15 +340,17 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
                 frame_blocking()
 
         def run_pipelined(k):
-            sim.set_state_begin(hp, hv)            # inputs of step 0
+            # (N > 1: every rank moves 1/N of the rows over its own PCIe link; the upload is completed by
+            # an all-gather over NVLink, each rank holds its rows of the frame)
+            sh.set_state_begin(hp, hv)             # inputs of step 0
             for i in range(k):
                 sh.set_state_commit()
                 if i + 1 < k:
-                    sim.set_state_begin(hp, hv)    # next step's inputs upload while this step computes
+                    sh.set_state_begin(hp, hv)     # next step's inputs upload while this step computes
                 sh.step(dt)
-                sim.frame_wait()                   # host buffers of frame i-1 are complete
-                sim.frame_begin(15.0, out_p[i & 1], out_c[i & 1])   # D2H overlaps the next step
-            sim.frame_wait()
+                sh.frame_wait()                    # host buffers of frame i-1 are complete
+                sh.frame_begin(15.0, out_p[i & 1], out_c[i & 1])    # D2H overlaps the next step
+            sh.frame_wait()
 
         def timed(fn):
             fn(1)

@@ -95,6 +95,15 @@ int b200_nbody_frame_wait(b200_nbody* h);
  * host arrays may be reused.  Started one step ahead, the copy overlaps the previous step's kernels. */
 int b200_nbody_set_state_begin(b200_nbody* h, const double* pos, const double* vel);
 int b200_nbody_set_state_commit(b200_nbody* h);
+/* Sharded host traffic (one process per GPU, every rank a replica): a rank uploads / downloads only rows
+ * [row_begin, row_end) of the creation-order arrays (the pointers are the FULL arrays' bases).  After
+ * set_state_begin_rows the caller makes the handle's stream wait for the copy (upload_wait), completes
+ * the device staging buffers (upload_staging: (n + 64, 3) fp64 each, padded for equal slices) with an
+ * all-gather over NVLink on that stream, then calls set_state_commit. */
+int b200_nbody_set_state_begin_rows(b200_nbody* h, const double* pos, const double* vel, int64_t row_begin, int64_t row_end);
+int b200_nbody_upload_staging(b200_nbody* h, void** pos_device_ptr, void** vel_device_ptr);
+int b200_nbody_upload_wait(b200_nbody* h);
+int b200_nbody_frame_begin_rows(b200_nbody* h, double max_speed, float* pos_out, float* col_out, int64_t row_begin, int64_t row_end);
 /* Sorted 63-bit Morton keys of the current state and the sort permutation
  * (perm[k] = creation index of the body at sorted position k). */
 int b200_nbody_get_keys(b200_nbody* h, uint64_t* out);

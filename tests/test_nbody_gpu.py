@@ -360,3 +360,18 @@ def test_sharded_sort_merge_is_bit_identical_to_the_full_sort(world):
     b.step_begin_sorted()
     assert np.array_equal(a.get_morton_keys(), b.get_morton_keys())
     assert np.array_equal(a.get_sort_permutation(), b.get_sort_permutation())
+
+
+def test_multi_gpu_replicas_match_unsharded_twin():
+    """torchrun x2 (NCCL): sharded traversal + sharded sort + sharded host traffic, every rank compared
+    step by step with an unsharded twin on its own GPU.  Needs two GPUs on the box."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "scripts", "mgpu_check.py"), "60001"]
+    res = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "MGPU CHECK PASSED" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
