@@ -20,7 +20,7 @@ class NBodyStats(C.Structure):
         ("bounds", C.c_double), ("error_flags", C.c_uint32), ("sm_count", C.c_int32),
         ("bytes_allocated", C.c_int64), ("timed_steps", C.c_int64), ("phase_ms", C.c_double * N_PHASES),
         ("pair_records", C.c_int64), ("trav_pair_slots", C.c_int64), ("trav_lane_pairs", C.c_int64),
-        ("trav_batches", C.c_int64), ("trav_stack_max", C.c_int64),
+        ("trav_batches", C.c_int64), ("trav_stack_max", C.c_int64), ("trav_shared_pairs", C.c_int64),
     ]
 
 

@@ -214,6 +214,7 @@ B200_API int b200_nbody_get_stats(b200_nbody* h, b200_nbody_stats* out)
         out->trav_lane_pairs = (int64_t)ctr[2];
         out->trav_batches = (int64_t)ctr[3];
         out->trav_stack_max = (int64_t)ctr[4];
+        out->trav_shared_pairs = (int64_t)ctr[5];
         out->error_flags = err;
         out->sm_count = s.sm_count;
         out->bytes_allocated = (int64_t)s.bytes_allocated;

@@ -594,6 +594,18 @@ __device__ __forceinline__ float rsqrt_approx(float x)
     return r;
 }
 
+// The MAC of both children of a pair for one lane: a lane inside the pair's mask accepts a child iff
+// d2 > T (one FSETP with the mask bit as its predicate operand); r = accept ? d2^-1/2 : 0.  The
+// ballots are of "not accepted" and still contain the lanes outside the mask: expand() removes them.
+__device__ __forceinline__ void mac_pair(float2 d2, float T0, float T1, bool in, unsigned& om0, unsigned& om1, float2& r)
+{
+    const bool a0 = in && d2.x > T0, a1 = in && d2.y > T1;
+    om0 = __ballot_sync(0xffffffffu, !a0);
+    om1 = __ballot_sync(0xffffffffu, !a1);
+    r.x = a0 ? rsqrt_approx(d2.x) : 0.f;
+    r.y = a1 ? rsqrt_approx(d2.y) : 0.f;
+}
+
 template <bool COUNT>
 __global__ void __launch_bounds__(TRAV_BLOCK, 4) traverse_kernel(const float4* __restrict__ recs, const float4* __restrict__ posm,
                                                                  float4* __restrict__ acc, int tile_begin, int tile_end, int n,
@@ -623,7 +635,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 4) traverse_kernel(const float4* _
         const int k = tile * 32 + (int)lane;
         const bool valid = k < n;
         const float4 p = valid ? posm[k] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float2 npy = make_float2(-p.y, -p.y), npz = make_float2(-p.z, -p.z);
+        const float2 npx = make_float2(-p.x, -p.x), npy = make_float2(-p.y, -p.y), npz = make_float2(-p.z, -p.z);
         float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;   // (even, odd) children accumulate separately
         int cnt = 0, lanepairs = 0, slots = 0;
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
@@ -671,24 +683,20 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 4) traverse_kernel(const float4* _
                 const float4 XY = sXY[j];
                 const float4 ZM = sZM[j];
                 const float4 TM = sTM[j];
-                const bool in = (__float_as_uint(TM.z) & lanebit) != 0u;
-                const float nqx = in ? -p.x : -REC_LANE_SENTINEL;
-                const float2 dx = __fadd2_rn(make_float2(XY.x, XY.y), make_float2(nqx, nqx));
+                const bool inbit = (__float_as_uint(TM.z) & lanebit) != 0u;
+                const float2 dx = __fadd2_rn(make_float2(XY.x, XY.y), npx);
                 const float2 dy = __fadd2_rn(make_float2(XY.z, XY.w), npy);
                 const float2 dz = __fadd2_rn(make_float2(ZM.x, ZM.y), npz);
                 const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, eps22)));
-                const bool o0 = d2.x <= TM.x, o1 = d2.y <= TM.y;
-                const unsigned om0 = __ballot_sync(0xffffffffu, o0);
-                const unsigned om1 = __ballot_sync(0xffffffffu, o1);
-                if (lane == 0) *reinterpret_cast<uint2*>(&sOP[j]) = make_uint2(om0, om1);
+                unsigned om0, om1;
                 float2 r;
-                r.x = o0 ? 0.f : rsqrt_approx(d2.x);
-                r.y = o1 ? 0.f : rsqrt_approx(d2.y);
+                mac_pair(d2, TM.x, TM.y, inbit, om0, om1, r);
+                if (lane == 0) *reinterpret_cast<uint2*>(&sOP[j]) = make_uint2(om0, om1);
                 if (COUNT) {
-                    if (in) {
+                    if (inbit) {
                         ++lanepairs;
-                        if (!o0 && XY.x < 2e18f) ++cnt;
-                        if (!o1 && XY.y < 2e18f) ++cnt;
+                        if (r.x != 0.f && XY.x < 2e18f) ++cnt;
+                        if (r.y != 0.f && XY.y < 2e18f) ++cnt;
                     }
                 }
                 const float2 f = __fmul2_rn(make_float2(ZM.z, ZM.w), __fmul2_rn(__fmul2_rn(r, r), r));
@@ -704,6 +712,8 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 4) traverse_kernel(const float4* _
             uint2 om = make_uint2(0u, 0u);
             if ((int)lane < P) {
                 om = *reinterpret_cast<const uint2*>(&sOP[lane]);
+                const unsigned mask = __float_as_uint(sTM[lane].z);   // the ballots include the lanes outside the mask
+                om.x &= mask; om.y &= mask;
                 const float4 fn = sFN[lane];
                 f0 = __float_as_uint(fn.x); f1 = __float_as_uint(fn.y);
                 n0 = __float_as_uint(fn.z); n1 = __float_as_uint(fn.w);
@@ -769,6 +779,260 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 4) traverse_kernel(const float4* _
         atomicAdd(&counters[2], w_lanepairs);
         atomicAdd(&counters[3], w_batches);
         atomicMax(&counters[4], (unsigned long long)w_spmax);
+    }
+}
+
+// ---------------------------------------------------------------------------- 64-body walk
+// The same walk with TWO bodies per lane: a warp owns 64 consecutive sorted bodies (lane l: bodies l
+// and l + 32 of the tile), a stack entry carries one lane mask per 32-body half.  A staged pair
+// record is read from shared memory once for both halves and the batch bookkeeping is shared, which
+// halves the shared-memory wavefronts and the walk overhead per evaluated pair.  A batch is sorted by
+// class -- pairs needed by both halves, only by the low half, only by the high half -- and each class
+// has its own loop, so a half never evaluates a pair none of its lanes asked for: the evaluated
+// (pair, half) set is exactly that of two independent 32-body walks, every lane still makes the
+// reference's per-body MAC decision.
+struct __align__(16) WarpShared64 {
+    unsigned stk_first[TRAV_CAP];        // pair index | (pairs - 1) << 29 (one pair, except chunks of a bucket)
+    unsigned stk_lo[TRAV_CAP];           // lanes whose body l opened the pair's parent cell
+    unsigned stk_hi[TRAV_CAP];           //                 body l + 32
+    float4 stage[5 * TRAV_AREA];         // XY ZM {T0,T1,mask lo,mask hi} FN {open lo 0, lo 1, hi 0, hi 1}
+};
+constexpr size_t TRAV64_SMEM_BYTES = sizeof(WarpShared64) * TRAV_WARPS;
+
+struct EvalBody {
+    float npx, npy, npz;                 // -position
+    float2 ax, ay, az;                   // (even, odd) children accumulate separately
+    int cnt, lanepairs;
+};
+
+template <bool COUNT>
+__device__ __forceinline__ void eval_pair(const float4& XY, const float4& ZM, float T0, float T1, unsigned mask, unsigned lanebit,
+                                          float2 eps22, EvalBody& b, unsigned& om0, unsigned& om1)
+{
+    const bool inbit = (mask & lanebit) != 0u;
+    const float2 dx = __fadd2_rn(make_float2(XY.x, XY.y), make_float2(b.npx, b.npx));
+    const float2 dy = __fadd2_rn(make_float2(XY.z, XY.w), make_float2(b.npy, b.npy));
+    const float2 dz = __fadd2_rn(make_float2(ZM.x, ZM.y), make_float2(b.npz, b.npz));
+    const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, eps22)));
+    float2 r;
+    mac_pair(d2, T0, T1, inbit, om0, om1, r);
+    if (COUNT) {
+        if (inbit) {
+            ++b.lanepairs;
+            if (r.x != 0.f && XY.x < 2e18f) ++b.cnt;
+            if (r.y != 0.f && XY.y < 2e18f) ++b.cnt;
+        }
+    }
+    const float2 f = __fmul2_rn(make_float2(ZM.z, ZM.w), __fmul2_rn(__fmul2_rn(r, r), r));
+    b.ax = __ffma2_rn(dx, f, b.ax);
+    b.ay = __ffma2_rn(dy, f, b.ay);
+    b.az = __ffma2_rn(dz, f, b.az);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRAV_BLOCK, 3) traverse64_kernel(const float4* __restrict__ recs, const float4* __restrict__ posm,
+                                                                   float4* __restrict__ acc, int begin, int end,
+                                                                   float eps2, float G, unsigned* tile_counter,
+                                                                   unsigned long long* counters, unsigned* error)
+{
+    extern __shared__ __align__(16) unsigned char trav_smem[];
+    const unsigned lane = lane_id();
+    const unsigned lanebit = 1u << lane;
+    const unsigned lt = lanemask_lt();
+    WarpShared64& ws = reinterpret_cast<WarpShared64*>(trav_smem)[threadIdx.x >> 5];
+    const float4* sXY = ws.stage;
+    const float4* sZM = ws.stage + TRAV_AREA;
+    const float4* sTM = ws.stage + 2 * TRAV_AREA;
+    const float4* sFN = ws.stage + 3 * TRAV_AREA;
+    uint4* sOP = reinterpret_cast<uint4*>(ws.stage + 4 * TRAV_AREA);
+    const float2 eps22 = make_float2(eps2, eps2);
+    unsigned long long w_inter = 0, w_slots = 0, w_lanepairs = 0, w_batches = 0, w_both = 0;
+    int w_spmax = 0;
+
+    for (;;) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1u);
+        t = __reduce_max_sync(0xffffffffu, t);   // (broadcast through a uniform register: the compiler can prove the walk convergent)
+        const int64_t base = (int64_t)begin + 64 * (int64_t)t;
+        if (base >= end) break;
+        const int ka = (int)base + (int)lane, kb = ka + 32;
+        const bool va = ka < end, vb = kb < end;
+        EvalBody A, B;
+        {
+            const float4 pa = va ? posm[ka] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 pb = vb ? posm[kb] : make_float4(0.f, 0.f, 0.f, 0.f);
+            A.npx = -pa.x; A.npy = -pa.y; A.npz = -pa.z;
+            B.npx = -pb.x; B.npy = -pb.y; B.npz = -pb.z;
+        }
+        A.ax = A.ay = A.az = B.ax = B.ay = B.az = make_float2(0.f, 0.f);
+        A.cnt = A.lanepairs = B.cnt = B.lanepairs = 0;
+        int slots_a = 0, slots_b = 0;
+        {
+            const unsigned vma = __ballot_sync(0xffffffffu, va), vmb = __ballot_sync(0xffffffffu, vb);
+            if (lane == 0) { ws.stk_first[0] = 0u; ws.stk_lo[0] = vma; ws.stk_hi[0] = vmb; }   // pair 0 = {root, dummy}
+        }
+        int sp = 1;
+        __syncwarp();
+        while (sp > 0) {
+            // ---- select: the top entries, one per lane, sorted by class (both | low only | high only)
+            const int idx = sp - 1 - (int)lane;
+            unsigned ef = 0, ml = 0, mh = 0;
+            if (idx >= 0) { ef = ws.stk_first[idx]; ml = ws.stk_lo[idx]; mh = ws.stk_hi[idx]; }
+            const unsigned multi = __ballot_sync(0xffffffffu, (ef >> 29) != 0u);
+            const bool chunk = (multi & 1u) != 0u;
+            const unsigned ef0 = __shfl_sync(0xffffffffu, ef, 0);
+            const unsigned ml0 = __shfl_sync(0xffffffffu, ml, 0), mh0 = __shfl_sync(0xffffffffu, mh, 0);
+            const int room = (TRAV_CAP - TRAV_RESERVE - sp) / 7;
+            int E = min(min(sp, TRAV_BATCH), max(room, 1));
+            if (multi) E = min(E, __ffs(multi) - 1);
+            const bool taken = (int)lane < E;
+            const unsigned bB = __ballot_sync(0xffffffffu, taken && ml != 0u && mh != 0u);
+            const unsigned bL = __ballot_sync(0xffffffffu, taken && mh == 0u);
+            int nB = __popc(bB), nL = __popc(bL), P = E;
+            int slot = (bB & lanebit) ? __popc(bB & lt) : (bL & lanebit) ? nB + __popc(bL & lt) : nB + nL + (int)lane - __popc((bB | bL) & lt);
+            if (chunk) {   // a chunk of a bucket is a batch of its own: P pairs of one class
+                E = 1;
+                P = (int)(ef0 >> 29) + 1;
+                nB = (ml0 != 0u && mh0 != 0u) ? P : 0;
+                nL = (mh0 == 0u) ? P : 0;
+            }
+            // (the max-reduces leave the trip counts in uniform registers: the loops below are provably convergent)
+            P = __reduce_max_sync(0xffffffffu, P);
+            nB = __reduce_max_sync(0xffffffffu, nB);
+            nL = __reduce_max_sync(0xffffffffu, nL);
+            const int top = sp - 1;
+            sp -= E;
+            // ---- load: 8 pair records (4 x 16 B each) per warp-wide load; entry e goes to its class slot
+#pragma unroll
+            for (int it = 0; it < TRAV_BATCH / 8; ++it) {
+                const int e = it * 8 + (int)(lane >> 2);
+                int sl = __shfl_sync(0xffffffffu, slot, e);
+                if (e < P) {
+                    unsigned first, mlo, mhi;
+                    if (chunk) { first = (ef0 & TRAV_FIRST_MASK) + (unsigned)e; mlo = ml0; mhi = mh0; sl = e; }
+                    else { first = ws.stk_first[top - e]; mlo = ws.stk_lo[top - e]; mhi = ws.stk_hi[top - e]; }
+                    float4 v = __ldg(&recs[4 * (int64_t)first + (lane & 3u)]);
+                    if ((lane & 3u) == 2u) { v.z = __uint_as_float(mlo); v.w = __uint_as_float(mhi); }
+                    ws.stage[(lane & 3u) * TRAV_AREA + sl] = v;
+                }
+            }
+            __syncwarp();
+            // ---- eval, one loop per class
+            const int jL = nB + nL;
+#pragma unroll 2
+            for (int j = 0; j < nB; ++j) {
+                const float4 XY = sXY[j];
+                const float4 ZM = sZM[j];
+                const float4 TM = sTM[j];
+                uint4 om;
+                eval_pair<COUNT>(XY, ZM, TM.x, TM.y, __float_as_uint(TM.z), lanebit, eps22, A, om.x, om.y);
+                eval_pair<COUNT>(XY, ZM, TM.x, TM.y, __float_as_uint(TM.w), lanebit, eps22, B, om.z, om.w);
+                if (lane == 0) sOP[j] = om;
+            }
+#pragma unroll 4
+            for (int j = nB; j < jL; ++j) {
+                const float4 XY = sXY[j];
+                const float4 ZM = sZM[j];
+                const float4 TM = sTM[j];
+                uint4 om = make_uint4(0u, 0u, 0u, 0u);
+                eval_pair<COUNT>(XY, ZM, TM.x, TM.y, __float_as_uint(TM.z), lanebit, eps22, A, om.x, om.y);
+                if (lane == 0) sOP[j] = om;
+            }
+#pragma unroll 4
+            for (int j = jL; j < P; ++j) {
+                const float4 XY = sXY[j];
+                const float4 ZM = sZM[j];
+                const float4 TM = sTM[j];
+                uint4 om = make_uint4(0u, 0u, 0u, 0u);
+                eval_pair<COUNT>(XY, ZM, TM.x, TM.y, __float_as_uint(TM.w), lanebit, eps22, B, om.z, om.w);
+                if (lane == 0) sOP[j] = om;
+            }
+            slots_a += jL;
+            slots_b += nB + (P - jL);
+            __syncwarp();
+            // ---- expand: lane j owns pair slot j
+            unsigned f0 = 0, f1 = 0, n0 = 0, n1 = 0;
+            uint4 om = make_uint4(0u, 0u, 0u, 0u);
+            if ((int)lane < P) {
+                om = sOP[lane];
+                const float4 tm = sTM[lane];   // the ballots include the lanes outside the masks
+                om.x &= __float_as_uint(tm.z); om.y &= __float_as_uint(tm.z);
+                om.z &= __float_as_uint(tm.w); om.w &= __float_as_uint(tm.w);
+                const float4 fn = sFN[lane];
+                f0 = __float_as_uint(fn.x); f1 = __float_as_uint(fn.y);
+                n0 = __float_as_uint(fn.z); n1 = __float_as_uint(fn.w);
+            }
+            const bool c0 = (om.x | om.z) != 0u && n0 != 0u, c1 = (om.y | om.w) != 0u && n1 != 0u;
+            const int np0 = c0 ? (int)((n0 + 1u) >> 1) : 0, np1 = c1 ? (int)((n1 + 1u) >> 1) : 0;
+            const bool big = np0 > TRAV_CELL_PAIRS || np1 > TRAV_CELL_PAIRS;
+            if (!__any_sync(0xffffffffu, big)) {
+                const unsigned k = (unsigned)(np0 + np1);
+                const unsigned b0 = __ballot_sync(0xffffffffu, (k & 1u) != 0u), b1 = __ballot_sync(0xffffffffu, (k & 2u) != 0u);
+                const unsigned b2 = __ballot_sync(0xffffffffu, (k & 4u) != 0u), b3 = __ballot_sync(0xffffffffu, (k & 8u) != 0u);
+                const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
+                if (sp + total > TRAV_CAP) {   // cannot happen (see the stack bound above); never drop silently
+                    if (lane == 0) atomicOr(error, (unsigned)ERR_STACK_OVERFLOW);
+                    sp = 0;
+                } else {
+                    int pos = sp + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) + 8 * __popc(b3 & lt);
+                    for (int q = 0; q < np0; ++q, ++pos) { ws.stk_first[pos] = f0 + (unsigned)q; ws.stk_lo[pos] = om.x; ws.stk_hi[pos] = om.z; }
+                    for (int q = 0; q < np1; ++q, ++pos) { ws.stk_first[pos] = f1 + (unsigned)q; ws.stk_lo[pos] = om.y; ws.stk_hi[pos] = om.w; }
+                    sp += total;
+                }
+            } else {
+                // rare: a bucket of > 8 bodies sharing one finest-level cell is pushed in chunks of <= 8 pairs
+                const int e0 = (np0 + TRAV_CHUNK_PAIRS - 1) / TRAV_CHUNK_PAIRS;
+                const int e1 = (np1 + TRAV_CHUNK_PAIRS - 1) / TRAV_CHUNK_PAIRS;
+                int inc2 = e0 + e1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, inc2, o);
+                    if ((int)lane >= o) inc2 += u;
+                }
+                const int total = __reduce_add_sync(0xffffffffu, e0 + e1);
+                if (sp + total > TRAV_CAP) {   // never drop silently
+                    if (lane == 0) atomicOr(error, (unsigned)ERR_STACK_OVERFLOW);
+                    sp = 0;
+                } else {
+                    int pos = sp + inc2 - (e0 + e1);
+                    for (int q = 0; q < e0; ++q, ++pos) {
+                        const int r = min(np0 - TRAV_CHUNK_PAIRS * q, TRAV_CHUNK_PAIRS);
+                        ws.stk_first[pos] = (f0 + (unsigned)(TRAV_CHUNK_PAIRS * q)) | ((unsigned)(r - 1) << 29);
+                        ws.stk_lo[pos] = om.x; ws.stk_hi[pos] = om.z;
+                    }
+                    for (int q = 0; q < e1; ++q, ++pos) {
+                        const int r = min(np1 - TRAV_CHUNK_PAIRS * q, TRAV_CHUNK_PAIRS);
+                        ws.stk_first[pos] = (f1 + (unsigned)(TRAV_CHUNK_PAIRS * q)) | ((unsigned)(r - 1) << 29);
+                        ws.stk_lo[pos] = om.y; ws.stk_hi[pos] = om.w;
+                    }
+                    sp += total;
+                }
+            }
+            sp = __reduce_max_sync(0xffffffffu, sp);   // uniform register: the walk loop is provably convergent
+            if (COUNT) { ++w_batches; w_both += (unsigned)nB; w_spmax = max(w_spmax, sp); }
+            __syncwarp();
+        }
+        // acc.w: exact interaction count (COUNT) or the half-tile's evaluated pair slots (a cost proxy)
+        if (va) acc[ka] = make_float4(G * (A.ax.x + A.ax.y), G * (A.ay.x + A.ay.y), G * (A.az.x + A.az.y), __int_as_float(COUNT ? A.cnt : slots_a));
+        if (vb) acc[kb] = make_float4(G * (B.ax.x + B.ax.y), G * (B.ay.x + B.ay.y), G * (B.az.x + B.az.y), __int_as_float(COUNT ? B.cnt : slots_b));
+        if (COUNT) {
+            unsigned c32 = (va ? (unsigned)A.cnt : 0u) + (vb ? (unsigned)B.cnt : 0u), l32 = (unsigned)(A.lanepairs + B.lanepairs);
+            for (int o = 16; o > 0; o >>= 1) {
+                c32 += __shfl_xor_sync(0xffffffffu, c32, o);
+                l32 += __shfl_xor_sync(0xffffffffu, l32, o);
+            }
+            w_inter += c32;
+            w_lanepairs += l32;
+            w_slots += (unsigned)(slots_a + slots_b);
+        }
+    }
+    if (COUNT && lane == 0) {
+        if (w_inter) atomicAdd(&counters[0], w_inter);
+        atomicAdd(&counters[1], w_slots);
+        atomicAdd(&counters[2], w_lanepairs);
+        atomicAdd(&counters[3], w_batches);
+        atomicMax(&counters[4], (unsigned long long)w_spmax);
+        atomicAdd(&counters[5], w_both);
     }
 }
 
@@ -1200,9 +1464,12 @@ void nbody_alloc(NBodySim& s, int n)
     B200_CHECK(cudaFuncSetAttribute(traverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV_SMEM_BYTES));
     B200_CHECK(cudaFuncSetAttribute(traverse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV_SMEM_BYTES));
     {
+        // B200_TRAV = 32 | 64 | t forces a walk; default: chosen per launch (see nbody_traverse)
         const char* mode = getenv("B200_TRAV");
-        s.trav_transposed = mode && mode[0] == 't';   // B200_TRAV=transposed: experimental 8-body walk (slower: see DESIGN.md)
+        s.trav_mode = !mode ? 0 : mode[0] == 't' ? 8 : mode[0] == '6' ? 64 : 32;
     }
+    B200_CHECK(cudaFuncSetAttribute(traverse64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV64_SMEM_BYTES));
+    B200_CHECK(cudaFuncSetAttribute(traverse64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV64_SMEM_BYTES));
     B200_CHECK(cudaMemset(s.colors, 0, 3 * N * sizeof(float)));
     s.shard_begin = 0;
     s.shard_end = n;
@@ -1489,7 +1756,11 @@ void nbody_traverse(NBodySim& s, int begin, int end)
         B200_CHECK(cudaMemsetAsync(s.d_tile_counter, 0, sizeof(unsigned), st));
         const int tiles = tile_end - tile_begin;
         const float eps2 = (float)(s.softening * s.softening);
-        if (s.trav_transposed) {
+        // Two bodies per lane pay off when neighbouring 32-body tiles share most of their interaction
+        // lists (large N, large theta: 0.90 of the pair evaluations are shared at 50 M / theta 0.7, 0.80 at
+        // 1 M / theta 0.5); measured on B200: -5 % at 50 M / 0.7, +5 % at 1 M / 0.5, break-even near 4 M / 0.7.
+        const int mode = s.trav_mode ? s.trav_mode : (s.theta >= 0.65 && s.n >= 8000000 ? 64 : 32);
+        if (mode == 8) {
             const int blocks = min(div_up(tiles, TRAV_WARPS), s.sm_count * 2);
             if (s.count_interactions)
                 traverse_t_kernel<true><<<blocks, TRAV_BLOCK, T2_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, tile_begin, tile_end, min(end, s.n),
@@ -1497,6 +1768,20 @@ void nbody_traverse(NBodySim& s, int begin, int end)
             else
                 traverse_t_kernel<false><<<blocks, TRAV_BLOCK, T2_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, tile_begin, tile_end, min(end, s.n),
                                                                                    eps2, (float)s.G, s.d_tile_counter, s.d_interactions, s.d_error);
+            ++s.launches;
+            B200_CHECK(cudaGetLastError());
+            s.timer.mark(st);
+            return;
+        }
+        if (mode == 64) {
+            const int tiles64 = div_up(min(end, s.n) - begin, 64);
+            const int blocks = min(div_up(tiles64, TRAV_WARPS), s.sm_count * 3);
+            if (s.count_interactions)
+                traverse64_kernel<true><<<blocks, TRAV_BLOCK, TRAV64_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, begin, min(end, s.n), eps2, (float)s.G,
+                                                                                      s.d_tile_counter, s.d_interactions, s.d_error);
+            else
+                traverse64_kernel<false><<<blocks, TRAV_BLOCK, TRAV64_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, begin, min(end, s.n), eps2, (float)s.G,
+                                                                                       s.d_tile_counter, s.d_interactions, s.d_error);
             ++s.launches;
             B200_CHECK(cudaGetLastError());
             s.timer.mark(st);

@@ -33,7 +33,9 @@ constexpr int TRAV_WARPS = TRAV_BLOCK / 32;
 constexpr int TRAV_BATCH = 32;       // pair slots evaluated per batch
 constexpr int TRAV_AREA = TRAV_BATCH + 2;   // entries between staging areas (bank offset of 32 B)
 constexpr int TRAV_CAP = 512;        // stack entries per warp (only cells that must be opened are pushed)
-constexpr int TRAV_DFS_MARK = 256;   // above this many entries a batch pops only the top one
+constexpr int TRAV_DFS_MARK = 256;   // 32-body walk: above this many entries a batch pops only the top one
+constexpr int TRAV_RESERVE = 160;    // stack room kept free by the batch size limit (>= the depth-first bound 7 * 21)
+constexpr int TRAV_CELL_PAIRS = 4;    // pairs of an ordinary cell (<= 8 children); more = a finest-level bucket
 constexpr int TRAV_COUNTERS = 8;     // interactions, pair slots, lane-pairs, batches, stack high-water
 
 enum NBodyPhase { PH_KEYGEN = 0, PH_SORT, PH_GATHER, PH_BUILD, PH_EXTRACT, PH_TRAVERSE, PH_EXCHANGE, PH_INTEGRATE, PH_COUNT };
@@ -86,7 +88,7 @@ struct NBodySim {
     float* colors = nullptr;                  // (N,3) f32, creation order
     void* stage = nullptr;                    // (N,3) f64-sized staging for getters
     bool tree_valid = false;                  // keys/perm/tree describe the current positions
-    bool trav_transposed = false;             // experimental 8-body transposed walk instead of the 32-body batched walk
+    int trav_mode = 0;                        // 0: per launch (64 for large N and theta, else 32); 32 / 64: forced; 8: experimental transposed walk
     bool count_interactions = false;          // exact per-body interaction counts in the traversal (slower)
 
     // multi-GPU: this rank traverses sorted bodies [shard_begin, shard_end) (multiples of 32)

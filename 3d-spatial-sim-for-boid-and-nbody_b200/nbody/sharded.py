@@ -13,7 +13,8 @@ from __future__ import annotations
 
 from typing import List, Tuple
 
-TILE = 32  # a warp owns 32 consecutive sorted bodies; slices are whole tiles
+TILE = 64  # a warp owns 64 consecutive sorted bodies (two per lane); slices are whole tiles, so a rank's
+           # tiles are tiles of the single-GPU pass and the accelerations are bit-identical
 
 
 def slice_size(n: int, world: int) -> int:

@@ -47,10 +47,11 @@ typedef struct b200_nbody_stats {
     double  phase_ms[B200_NBODY_PHASES];
     int64_t pair_records;      /* 64-byte pair records allocated for the last tree */
     /* traversal work counters since the last reset (only while counting is on) */
-    int64_t trav_pair_slots;   /* pair records evaluated by warps (each = 2 children x 32 lanes) */
+    int64_t trav_pair_slots;   /* (pair record, 32-body half tile) evaluations (each = 2 children x 32 lanes) */
     int64_t trav_lane_pairs;   /* (lane, pair) evaluations where the lane was in the pair's mask */
     int64_t trav_batches;      /* select/load/eval/expand rounds */
     int64_t trav_stack_max;    /* high-water mark of a warp's stack (capacity 512) */
+    int64_t trav_shared_pairs; /* pair records evaluated for both 32-body halves of a 64-body tile from one staging */
 } b200_nbody_stats;
 
 const char* b200_last_error(void);

@@ -26,7 +26,7 @@ def test_struct_sizes_match_header_layout():
     from b200sim import _lib
     import ctypes as C
     assert C.sizeof(_lib.BoidsParams) == 11 * 8
-    assert C.sizeof(_lib.NBodyStats) == 8 * 5 + 4 + 4 + 8 + 8 + 8 * 8 + 8 + 4 * 8
+    assert C.sizeof(_lib.NBodyStats) == 8 * 5 + 4 + 4 + 8 + 8 + 8 * 8 + 8 + 5 * 8
     assert C.sizeof(_lib.BoidsStats) == 8 * 3 + 4 + 4 + 8 * 2 + 8 * 4 + 8 * 5
 
 
@@ -100,14 +100,14 @@ def test_synthetic_generators_are_seeded_and_shaped():
 
 def test_partition_covers_all_bodies_in_whole_tiles():
     from b200sim.nbody import sharded
-    for n in (0, 1, 31, 32, 33, 1000, 50_000_000, 1_000_003):
+    for n in (0, 1, 31, 32, 33, 63, 64, 65, 1000, 50_000_000, 1_000_003):
         for world in (1, 2, 3, 4, 8):
             parts = sharded.partition_equal(n, world)
             assert parts[0][0] == 0 and parts[-1][1] == n
             for (b0, e0), (b1, e1) in zip(parts, parts[1:]):
                 assert e0 == b1
             for b, e in parts:
-                assert b <= e and (b % 32 == 0 or b == e)
+                assert b <= e and (b % 64 == 0 or b == e)
             assert sharded.slice_size(n, world) * world >= n
 
 
