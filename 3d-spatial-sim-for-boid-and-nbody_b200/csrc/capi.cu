@@ -282,6 +282,13 @@ B200_API int b200_nbody_frame_begin(b200_nbody* h, double max_speed, float* pos_
     B200_TRY(b200::nbody_frame_begin(h->sim, max_speed, pos_out, col_out))
 }
 
+B200_API int b200_nbody_frame_delta_begin(b200_nbody* h, double max_speed, int16_t* pos_delta_out, int16_t* col_delta_out)
+{
+    B200_ARG(h && ((pos_delta_out && col_delta_out) || h->sim.n == 0), "null argument");
+    B200_ARG(max_speed > 0.0, "max_speed must be > 0");
+    B200_TRY(b200::nbody_frame_delta_begin(h->sim, max_speed, pos_delta_out, col_delta_out))
+}
+
 B200_API int b200_nbody_frame_wait(b200_nbody* h)
 {
     B200_ARG(h, "handle is null");

@@ -1995,6 +1995,7 @@ static void async_free(NBodySim& s)
     cudaStreamSynchronize(s.up_stream);
     cudaStreamSynchronize(s.down_stream);
     cudaFree(s.frame_pos); cudaFree(s.frame_col); cudaFree(s.up_pos); cudaFree(s.up_vel);
+    if (s.frame_dpos) { cudaFree(s.frame_dpos); cudaFree(s.frame_dcol); s.frame_dpos = s.frame_dcol = nullptr; }
     cudaEventDestroy(s.ev_frame_ready); cudaEventDestroy(s.ev_frame_done);
     cudaEventDestroy(s.ev_upload_done); cudaEventDestroy(s.ev_upload_consumed);
     cudaStreamDestroy(s.up_stream); cudaStreamDestroy(s.down_stream);
@@ -2039,6 +2040,65 @@ void nbody_frame_begin_rows(NBodySim& s, double max_speed, float* host_pos, floa
         B200_CHECK(cudaMemcpyAsync(host_pos + off, s.frame_pos + off, bytes, cudaMemcpyDeviceToHost, s.down_stream));
         B200_CHECK(cudaMemcpyAsync(host_col + off, s.frame_col + off, bytes, cudaMemcpyDeviceToHost, s.down_stream));
     }
+    B200_CHECK(cudaEventRecord(s.ev_frame_done, s.down_stream));
+    s.frame_pending = true;
+    s.frame_has_prev = true;
+}
+
+// ---------------------------------------------------------------------------- delta frames (frame codec)
+// The recorder's on-disk format 2 stores a frame as int16((frame - previous frame) * 1000) per component
+// (tools/record.py:254-262), computed on float32 frames.  Producing the deltas on the device halves the
+// device-to-host bytes of a frame (12 instead of 24 B/body); the float32 staging of the last frame is
+// the "previous frame" and is updated in place.
+__device__ __forceinline__ short delta_i16(float cur, float prev)
+{
+    // numpy: ((cur - prev) * 1000).astype(int16) on float32 arrays = truncation through a 32-bit integer
+    // (cvttss2si: "integer indefinite" 0x80000000 outside the int32 range), then the low 16 bits
+    const float x = __fmul_rn(__fsub_rn(cur, prev), 1000.0f);
+    const int v = fabsf(x) < 2147483648.0f ? __float2int_rz(x) : (int)0x80000000;
+    return (short)(unsigned short)((unsigned)v & 0xffffu);
+}
+
+__global__ void __launch_bounds__(256) frame_delta_kernel(const double* __restrict__ pos, const double* __restrict__ vel,
+                                                          const uint32_t* __restrict__ id, float* __restrict__ fpos,
+                                                          float* __restrict__ fcol, short* __restrict__ dpos,
+                                                          short* __restrict__ dcol, int n, double max_speed)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t o = 3 * (int64_t)k, w = 3 * (int64_t)id[k];
+    const double vx = vel[o], vy = vel[o + 1], vz = vel[o + 2];
+    float c[3];
+    speed_color(fmin(1.0, sqrt(vx * vx + vy * vy + vz * vz) / max_speed), c[0], c[1], c[2]);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float p = (float)pos[o + a];
+        dpos[w + a] = delta_i16(p, fpos[w + a]);
+        dcol[w + a] = delta_i16(c[a], fcol[w + a]);
+        fpos[w + a] = p;
+        fcol[w + a] = c[a];
+    }
+}
+
+void nbody_frame_delta_begin(NBodySim& s, double max_speed, short* host_dpos, short* host_dcol)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    if (s.n == 0) return;
+    B200_REQUIRE(s.frame_has_prev, "frame_delta_begin needs a previous frame (call frame_begin first)");
+    const size_t N = (size_t)s.n;
+    if (!s.frame_dpos) {
+        s.frame_dpos = alloc_counted<short>(s, 3 * N);
+        s.frame_dcol = alloc_counted<short>(s, 3 * N);
+    }
+    if (s.frame_pending) B200_CHECK(cudaStreamWaitEvent(s.stream, s.ev_frame_done, 0));   // staging still being read
+    frame_delta_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.pos[s.cur], s.vel[s.cur], s.id[s.cur], s.frame_pos, s.frame_col,
+                                                               s.frame_dpos, s.frame_dcol, s.n, max_speed);
+    ++s.launches;
+    B200_CHECK(cudaGetLastError());
+    B200_CHECK(cudaEventRecord(s.ev_frame_ready, s.stream));
+    B200_CHECK(cudaStreamWaitEvent(s.down_stream, s.ev_frame_ready, 0));
+    B200_CHECK(cudaMemcpyAsync(host_dpos, s.frame_dpos, 3 * N * sizeof(short), cudaMemcpyDeviceToHost, s.down_stream));
+    B200_CHECK(cudaMemcpyAsync(host_dcol, s.frame_dcol, 3 * N * sizeof(short), cudaMemcpyDeviceToHost, s.down_stream));
     B200_CHECK(cudaEventRecord(s.ev_frame_done, s.down_stream));
     s.frame_pending = true;
 }

@@ -100,6 +100,8 @@ struct NBodySim {
     cudaEvent_t ev_frame_ready = nullptr, ev_frame_done = nullptr;     // device staging filled / D2H finished
     cudaEvent_t ev_upload_done = nullptr, ev_upload_consumed = nullptr; // H2D finished / staging read by the commit
     float *frame_pos = nullptr, *frame_col = nullptr;                  // (N,3) f32 staging, creation order
+    short *frame_dpos = nullptr, *frame_dcol = nullptr;                // (N,3) int16 delta staging (frame codec), lazily allocated
+    bool frame_has_prev = false;                                       // frame_pos / frame_col hold the previous frame
     double *up_pos = nullptr, *up_vel = nullptr;                       // (N,3) f64 staging of a prefetched state
     bool frame_pending = false, upload_pending = false;
 
@@ -148,6 +150,7 @@ void nbody_get_perm(NBodySim& s, uint32_t* out);
 void nbody_frame_begin(NBodySim& s, double max_speed, float* host_pos, float* host_col);
 void nbody_frame_begin_rows(NBodySim& s, double max_speed, float* host_pos, float* host_col, int row_begin, int row_end);
 void nbody_frame_wait(NBodySim& s);
+void nbody_frame_delta_begin(NBodySim& s, double max_speed, short* host_dpos, short* host_dcol);
 // state prefetch: H2D on a third stream into staging; commit swaps it in on the compute stream
 void nbody_set_state_begin(NBodySim& s, const double* pos, const double* vel);
 void nbody_set_state_begin_rows(NBodySim& s, const double* pos, const double* vel, int row_begin, int row_end);

@@ -189,6 +189,16 @@ class B200BarnesHutSimulation:
             _lib.check(self._L.b200_nbody_frame_begin_rows(self._handle(), float(max_speed), op.ctypes.data_as(fp),
                                                            oc.ctypes.data_as(fp), int(rows[0]), int(rows[1])))
 
+    def frame_delta_begin(self, max_speed: float, out_pos_delta: np.ndarray, out_col_delta: np.ndarray):
+        """The next frame as the recorder's format-2 payload: int16((frame - previous frame) * 1000),
+        positions and colours, creation order (tools/record.py:254-262), computed on the device; half
+        the device-to-host bytes of ``frame_begin``.  Needs a previous ``frame_begin``/``frame_delta_begin``."""
+        dp = self._out(out_pos_delta, (self.n, 3), np.int16)
+        dc = self._out(out_col_delta, (self.n, 3), np.int16)
+        self._frame_refs = (dp, dc)
+        ip = C.POINTER(C.c_int16)
+        _lib.check(self._L.b200_nbody_frame_delta_begin(self._handle(), float(max_speed), dp.ctypes.data_as(ip), dc.ctypes.data_as(ip)))
+
     def frame_wait(self):
         _lib.check(self._L.b200_nbody_frame_wait(self._handle()))
         self._frame_refs = None

@@ -91,6 +91,11 @@ int b200_nbody_set_params(b200_nbody* h, double G, double softening, double damp
  * untouched until frame_wait returns.  At most one frame is in flight. */
 int b200_nbody_frame_begin(b200_nbody* h, double max_speed, float* pos_out, float* col_out);
 int b200_nbody_frame_wait(b200_nbody* h);
+/* Delta frame for the recorder's on-disk format 2 (the arithmetic of compress_frame,
+ * tools/record.py:254-262): int16((frame - previous frame) * 1000) per component, float32 arithmetic, for
+ * positions and colours in creation order; "previous frame" = the frame of the last frame_begin /
+ * frame_delta_begin.  Half the device-to-host bytes of frame_begin.  Completed by frame_wait. */
+int b200_nbody_frame_delta_begin(b200_nbody* h, double max_speed, int16_t* pos_delta_out, int16_t* col_delta_out);
 /* Asynchronous set_state: begin starts the host-to-device copies on a third stream into staging;
  * commit waits for them, then makes them the current state on the handle's stream; after commit the
  * host arrays may be reused.  Started one step ahead, the copy overlaps the previous step's kernels. */

@@ -41,6 +41,48 @@ def _stub_opengl() -> None:
     sys.modules.update({"OpenGL": ogl, "OpenGL.GL": gl, "OpenGL.arrays": arrays, "OpenGL.arrays.vbo": vbo})
 
 
+def _stub_zstandard() -> None:
+    """tools/record.py:228 hard-imports `zstandard` (not installed): a minimal shim over the system
+    libzstd (the same binding the product's codec uses) with the two classes the recorder touches."""
+    if "zstandard" in sys.modules:
+        return
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import b200sim  # noqa: F401
+    from b200sim import codec
+
+    class ZstdCompressor:
+        def __init__(self, level=3, threads=0, **_kw):
+            self.level = level
+
+        def compress(self, data):
+            return codec.zstd_compress(bytes(data), self.level, 0)
+
+    class ZstdDecompressor:
+        def decompress(self, data, max_output_size=0):
+            return codec.zstd_decompress(bytes(data))
+
+    m = types.ModuleType("zstandard")
+    m.ZstdCompressor, m.ZstdDecompressor = ZstdCompressor, ZstdDecompressor
+    m.__version__ = "shim-libzstd-" + codec.zstd_version()
+    sys.modules["zstandard"] = m
+
+
+def load_recorder():
+    """The reference's frame codec functions, unmodified (tools/record.py:88-326)."""
+    if not available():
+        raise RuntimeError(f"reference tree not present at {REFERENCE_ROOT}")
+    _stub_opengl()
+    _stub_zstandard()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import importlib
+    rec = importlib.import_module("tools.record")
+    return types.SimpleNamespace(compress_frame=rec.compress_frame, decompress_frame=rec.decompress_frame,
+                                 load_frame=rec.load_frame, save_frame=rec.save_frame, module=rec)
+
+
 def load():
     """Returns a namespace with the reference's hot-path functions."""
     if not available():

@@ -361,6 +361,48 @@ def test_async_frame_and_state_prefetch_match_blocking_calls():
         b.set_state_commit()                       # nothing pending
 
 
+def test_device_delta_frames_are_the_recorders_format2_payload(tmp_path):
+    """Frame codec: int16 deltas produced on the device equal the recorder's host
+    arithmetic int16((frame - prev) * 1000) on the float32 frames (tools/record.py:256-262), bit for
+    bit; written through FrameWriter they decode (load_frame) to the frames within 1e-3."""
+    from b200sim import codec, presets
+    n = 50_021
+    pos, vel, mass = presets.generate("galaxy", n, 300.0, 0.1, 9)
+    sim = _sim(pos, vel, mass, 0.1, 2.0, theta=0.8)
+    with pytest.raises(Exception):
+        sim.frame_delta_begin(15.0, np.empty((n, 3), np.int16), np.empty((n, 3), np.int16))   # no previous frame
+    p0, c0 = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+    sim.step(0.1)
+    sim.frame_begin(15.0, p0, c0); sim.frame_wait()
+    w = codec.FrameWriter(tmp_path, level=3)
+    w.submit_absolute(0, p0, c0)
+    prev = (p0.copy(), c0.copy())
+    frames = [prev]
+    for k in range(1, 4):
+        for _ in range(2):
+            sim.step(0.1)
+        dp, dc = np.empty((n, 3), np.int16), np.empty((n, 3), np.int16)
+        sim.frame_delta_begin(15.0, dp, dc); sim.frame_wait()
+        sim.compute_colors(15.0)
+        cur = (sim.get_positions(), sim.get_colors())
+        assert np.array_equal(dp, codec.delta_payload(cur[0], prev[0]))
+        assert np.array_equal(dc, codec.delta_payload(cur[1], prev[1]))
+        assert np.abs(dp).max() > 0
+        w.submit_delta(k, dp, dc)
+        prev = cur
+        frames.append(cur)
+    w.close()
+    p3, c3 = codec.load_frame(tmp_path, 3)
+    assert np.abs(p3 - frames[3][0]).max() <= 3 * 1.001e-3 + 1e-4 and np.abs(c3 - frames[3][1]).max() <= 3 * 1.001e-3
+    # a frame_begin in between restarts the chain from an absolute frame
+    sim.step(0.1)
+    sim.frame_begin(15.0, p0, c0); sim.frame_wait()
+    sim.step(0.1)
+    dp, dc = np.empty((n, 3), np.int16), np.empty((n, 3), np.int16)
+    sim.frame_delta_begin(15.0, dp, dc); sim.frame_wait()
+    assert np.array_equal(dp, codec.delta_payload(sim.get_positions(), p0))
+
+
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_sharded_sort_merge_is_bit_identical_to_the_full_sort(world):
     """Multi-GPU sort path on one device: every 'rank' sorts one slice of the Morton-ordered state, the
