@@ -352,6 +352,23 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
                 sh.frame_begin(15.0, out_p[i & 1], out_c[i & 1])    # D2H overlaps the next step
             sh.frame_wait()
 
+        out_dp = [torch.empty((n, 3), dtype=torch.int16).pin_memory().numpy() for _ in range(2)]
+        out_dc = [torch.empty((n, 3), dtype=torch.int16).pin_memory().numpy() for _ in range(2)]
+
+        def run_pipelined_delta(k):
+            # the same loop with the frame as the recorder's format-2 payload (int16 deltas produced on the
+            # device): 12 instead of 24 B/body device-to-host.  Single GPU only.
+            sim.frame_begin(15.0, out_p[0], out_c[0]); sim.frame_wait()      # the chain's absolute frame
+            sh.set_state_begin(hp, hv)
+            for i in range(k):
+                sh.set_state_commit()
+                if i + 1 < k:
+                    sh.set_state_begin(hp, hv)
+                sh.step(dt)
+                sim.frame_wait()
+                sim.frame_delta_begin(15.0, out_dp[i & 1], out_dc[i & 1])
+            sim.frame_wait()
+
         def timed(fn):
             fn(1)
             if world > 1:
@@ -367,11 +384,15 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
 
         v_block = timed(run_blocking)
         v_pipe = timed(run_pipelined)
+        v_delta = timed(run_pipelined_delta) if world == 1 else None
         out["e2e"] = {"value": v_pipe, "unit": "body-updates/s", "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 24 * n,
                       "steps": e2e_steps,
                       "what": "per step, through the ctypes C-ABI with pinned HOST buffers: set_state_begin/commit (H2D of "
                               "positions + velocities) + step + frame_begin/wait (colours, D2H of positions + colours); the "
                               "copies run on side streams and overlap the neighbouring steps' kernels",
+                      "delta_frames_value": v_delta,
+                      "delta_frames_what": "same loop with frame_delta_begin (the recorder's int16 delta payload, computed on the "
+                                           "device): 12 B/body device-to-host per step instead of 24",
                       "blocking_value": v_block,
                       "blocking_what": "same bytes with the reference-style blocking calls: set_state + step + compute_colors + "
                                        "get_positions + get_colors"}
