@@ -25,14 +25,29 @@ __global__ void __launch_bounds__(256) boids_cells_kernel(const double* __restri
     keys[i] = (uint32_t)(cx + cy * dim + cz * dim * dim);   // x fastest (boids/flock.py:27)
 }
 
+constexpr int TABLE_CHUNK_LOG2 = 12;
+constexpr int TABLE_CHUNK = 1 << TABLE_CHUNK_LOG2;   // cells of the table built by one CTA
+constexpr int TABLE_PER_THREAD = TABLE_CHUNK / 256;
+
 __global__ void __launch_bounds__(256) boids_gather_kernel(const uint32_t* __restrict__ perm,
                                                            const double* __restrict__ pos_in, const double* __restrict__ vel_in,
                                                            const double* __restrict__ col_in, const uint32_t* __restrict__ id_in,
                                                            double* __restrict__ pos_out, double* __restrict__ vel_out,
-                                                           double* __restrict__ col_out, uint32_t* __restrict__ id_out, int n)
+                                                           double* __restrict__ col_out, uint32_t* __restrict__ id_out, int n,
+                                                           const uint32_t* __restrict__ sorted_keys, int nchunks,
+                                                           int* __restrict__ chunk_lb)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
+    // lower bound of every TABLE_CHUNK-cell chunk of the cell table (boids_table_kernel), from the
+    // boundaries of the sorted keys: chunk_lb[b] = first sorted position whose cell is in chunk >= b
+    {
+        const int cb = (int)(sorted_keys[k] >> TABLE_CHUNK_LOG2);
+        const int pb = k > 0 ? (int)(sorted_keys[k - 1] >> TABLE_CHUNK_LOG2) : -1;
+        for (int b = pb + 1; b <= cb; ++b) chunk_lb[b] = k;
+        if (k == n - 1)
+            for (int b = cb + 1; b <= nchunks; ++b) chunk_lb[b] = n;
+    }
     const int64_t j = 3 * (int64_t)perm[k], o = 3 * (int64_t)k;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -43,15 +58,55 @@ __global__ void __launch_bounds__(256) boids_gather_kernel(const uint32_t* __res
     id_out[k] = id_in[perm[k]];
 }
 
-// boids/flock.py:47-65: first sorted position (and here also the end) of every occupied cell
-__global__ void __launch_bounds__(256) boids_table_kernel(const uint32_t* __restrict__ sorted_keys, int n,
-                                                          int* __restrict__ cell_start, int* __restrict__ cell_end)
+// build_cell_lists (boids/flock.py:47-65) as ONE lower-bound table: first[c] = sorted position of the first
+// boid whose cell index is >= c, for every cell c in [0, C] (first[C] = n).  The boids of the cells
+// [a, b] (consecutive indices = a grid row segment) are then the run [first[a], first[b + 1]): two loads
+// per row instead of a start and an end per cell, and no memset.  A CTA owns TABLE_CHUNK consecutive
+// cells: its boids are the run between two chunk lower bounds (written by the gather kernel at the
+// chunk boundaries of the sorted keys); it marks the cell starts in shared memory and finishes with a
+// suffix-min scan seeded by the next chunk's lower bound.
+
+__global__ void __launch_bounds__(256) boids_table_kernel(const uint32_t* __restrict__ sorted_keys, int n, int64_t num_cells,
+                                                          const int* __restrict__ chunk_lb, int* __restrict__ first)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const uint32_t c = sorted_keys[k];
-    if (k == 0 || sorted_keys[k - 1] != c) cell_start[c] = k;
-    if (k == n - 1 || sorted_keys[k + 1] != c) cell_end[c] = k + 1;
+    __shared__ int sf[TABLE_CHUNK];
+    __shared__ int s_warp[8];
+    const int64_t c0 = (int64_t)blockIdx.x * TABLE_CHUNK;
+    const int tid = threadIdx.x;
+    const int kb = chunk_lb[blockIdx.x], ke = chunk_lb[blockIdx.x + 1];   // this chunk's boids (boids_gather_kernel)
+    for (int i = tid; i < TABLE_CHUNK; i += 256) sf[i] = 0x7fffffff;
+    __syncthreads();
+    for (int k = kb + tid; k < ke; k += 256) {
+        const uint32_t c = sorted_keys[k];
+        if (k == 0 || sorted_keys[k - 1] != c) sf[(int)((int64_t)c - c0)] = k;
+    }
+    __syncthreads();
+    // suffix-min: thread t owns cells [t*16, t*16+16)
+    int loc[TABLE_PER_THREAD];
+    int run = 0x7fffffff;
+#pragma unroll
+    for (int i = TABLE_PER_THREAD - 1; i >= 0; --i) {
+        run = min(run, sf[tid * TABLE_PER_THREAD + i]);
+        loc[i] = run;
+    }
+    // exclusive suffix-min of the threads' totals: later lanes, later warps, then the next chunk's bound
+    int inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_down_sync(0xffffffffu, inc, o);
+        if ((int)lane_id() + o < 32) inc = min(inc, v);
+    }
+    if (lane_id() == 0) s_warp[tid >> 5] = inc;
+    int after = __shfl_down_sync(0xffffffffu, inc, 1);
+    if (lane_id() == 31) after = 0x7fffffff;
+    __syncthreads();
+    for (int w = (tid >> 5) + 1; w < 8; ++w) after = min(after, s_warp[w]);
+    after = min(after, ke);
+#pragma unroll
+    for (int i = 0; i < TABLE_PER_THREAD; ++i) {
+        const int64_t c = c0 + tid * TABLE_PER_THREAD + i;
+        if (c <= num_cells) first[c] = min(loc[i], after);
+    }
 }
 
 // boids/flock.py:179-193 / :200-214 / :220-234: normalise to max_speed, subtract own velocity,
@@ -80,7 +135,7 @@ __device__ __forceinline__ void steer(double x, double y, double z, double vx, d
 // (x fastest), so their boids are ONE contiguous run of the sorted state.
 __global__ void __launch_bounds__(128) boids_rules_kernel(
     const double* __restrict__ pos_in, const double* __restrict__ vel_in, const double* __restrict__ col_in,
-    const uint32_t* __restrict__ id_in, const int* __restrict__ cell_start, const int* __restrict__ cell_end,
+    const uint32_t* __restrict__ id_in, const int* __restrict__ cell_first,
     double* __restrict__ pos_out, double* __restrict__ vel_out, double* __restrict__ col_out, uint32_t* __restrict__ id_out,
     int n, BoidsParams P, double offset, double cell, int dim, int R, double dt, double blend,
     unsigned long long* __restrict__ pairs)
@@ -103,14 +158,7 @@ __global__ void __launch_bounds__(128) boids_rules_kernel(
         for (int ncz = max(cz - R, 0); ncz <= min(cz + R, dim - 1); ++ncz) {
             for (int ncy = max(cy - R, 0); ncy <= min(cy + R, dim - 1); ++ncy) {
                 const int64_t row = (int64_t)ncy * dim + (int64_t)ncz * dim * dim;
-                int s = -1, e = -1;
-                for (int x = x0; x <= x1; ++x) {
-                    const int st = cell_start[row + x];
-                    if (st >= 0) {
-                        if (s < 0) s = st;
-                        e = cell_end[row + x];
-                    }
-                }
+                const int s = cell_first[row + x0], e = cell_first[row + x1 + 1];   // the row segment is one run
                 for (int j = s; j < e; ++j) {
                     if (j == k) continue;
                     const int64_t q = 3 * (int64_t)j;
@@ -227,8 +275,9 @@ void boids_alloc(BoidsSim& s, int n)
     }
     s.sorter.init(n);
     s.bytes_allocated += s.sorter.bytes();
-    s.cell_start = balloc<int>(s, (size_t)s.num_cells);
-    s.cell_end = balloc<int>(s, (size_t)s.num_cells);
+    s.cell_first = balloc<int>(s, (size_t)s.num_cells + 1);
+    s.table_chunks = (int)((s.num_cells + 1 + TABLE_CHUNK - 1) / TABLE_CHUNK);
+    s.chunk_lb = balloc<int>(s, (size_t)s.table_chunks + 1);
     s.d_pairs = balloc<unsigned long long>(s, 1);
     s.stage = balloc<double>(s, 3 * N);
     B200_CHECK(cudaMemset(s.d_pairs, 0, sizeof(unsigned long long)));
@@ -244,7 +293,7 @@ void boids_free(BoidsSim& s)
         cudaFree(s.keys[b]); cudaFree(s.vals[b]);
     }
     s.sorter.destroy();
-    cudaFree(s.cell_start); cudaFree(s.cell_end); cudaFree(s.d_pairs); cudaFree(s.stage);
+    cudaFree(s.cell_first); cudaFree(s.chunk_lb); cudaFree(s.d_pairs); cudaFree(s.stage);
     s.timer.destroy();
     if (s.stream) cudaStreamDestroy(s.stream);
     s.stream = nullptr;
@@ -281,15 +330,14 @@ void boids_step(BoidsSim& s, double dt)
     s.timer.mark(st);
     const int o = s.cur ^ 1;
     boids_gather_kernel<<<grid, 256, 0, st>>>(s.vals[slot], s.pos[s.cur], s.vel[s.cur], s.col[s.cur], s.id[s.cur],
-                                              s.pos[o], s.vel[o], s.col[o], s.id[o], n);
+                                              s.pos[o], s.vel[o], s.col[o], s.id[o], n, s.keys[slot], s.table_chunks, s.chunk_lb);
     ++s.launches;
     s.timer.mark(st);
-    B200_CHECK(cudaMemsetAsync(s.cell_start, 0xff, (size_t)s.num_cells * sizeof(int), st));
-    boids_table_kernel<<<grid, 256, 0, st>>>(s.keys[slot], n, s.cell_start, s.cell_end);
+    boids_table_kernel<<<s.table_chunks, 256, 0, st>>>(s.keys[slot], n, s.num_cells, s.chunk_lb, s.cell_first);
     ++s.launches;
     s.timer.mark(st);
     const double blend = fmin(1.0, s.p.color_blend_rate * dt);   // boids/flock.py:662
-    boids_rules_kernel<<<div_up(n, 128), 128, 0, st>>>(s.pos[o], s.vel[o], s.col[o], s.id[o], s.cell_start, s.cell_end,
+    boids_rules_kernel<<<div_up(n, 128), 128, 0, st>>>(s.pos[o], s.vel[o], s.col[o], s.id[o], s.cell_first,
                                                        s.pos[s.cur], s.vel[s.cur], s.col[s.cur], s.id[s.cur], n, s.p,
                                                        s.grid_offset, s.cell_size, s.grid_dim, s.cell_range, dt, blend,
                                                        s.d_pairs);

@@ -8,7 +8,7 @@
 //             physically reordered into cell order (gather A->B) and the fused rules+physics
 //             kernel reads B (neighbours are contiguous runs) and writes the updated state to A.
 //   keys[2]/vals[2]  cell index per boid (u32) + permutation, radix-sort ping-pong
-//   cell_start, cell_end (C) i32: sorted-position range of every occupied cell (start = -1: empty)
+//   cell_first (C + 1) i32: sorted position of the first boid whose cell index is >= c (lower-bound table)
 #pragma once
 #include "common.cuh"
 #include "radix_sort.cuh"
@@ -43,8 +43,9 @@ struct BoidsSim {
     uint32_t* keys[2] = {nullptr, nullptr};
     uint32_t* vals[2] = {nullptr, nullptr};
     rsort::Sorter<uint32_t> sorter;
-    int* cell_start = nullptr;
-    int* cell_end = nullptr;
+    int* cell_first = nullptr;
+    int* chunk_lb = nullptr;     // (table_chunks + 1) lower bound of every 4096-cell chunk of the table
+    int table_chunks = 0;
     unsigned long long* d_pairs = nullptr;   // accepted neighbour pairs (device-counted)
     double* stage = nullptr;
 
