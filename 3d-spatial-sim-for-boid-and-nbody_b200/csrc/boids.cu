@@ -133,13 +133,16 @@ __device__ __forceinline__ void steer(double x, double y, double z, double vx, d
 // compute_flocking_spatial (boids/flock.py:68-238) fused with update_physics_numba (:241-308).
 // One thread per boid in cell order; the (2R+1) cells of a grid row are consecutive cell indices
 // (x fastest), so their boids are ONE contiguous run of the sorted state.
-__global__ void __launch_bounds__(128) boids_rules_kernel(
+template <int RT>   // RT = 1: perception radius <= cell size (the reference's default grid), 3 x 3 rows unrolled with all
+                    // table loads issued up front; RT = 0: any cell range R
+__global__ void __launch_bounds__(128, 6) boids_rules_kernel(
     const double* __restrict__ pos_in, const double* __restrict__ vel_in, const double* __restrict__ col_in,
     const uint32_t* __restrict__ id_in, const int* __restrict__ cell_first,
     double* __restrict__ pos_out, double* __restrict__ vel_out, double* __restrict__ col_out, uint32_t* __restrict__ id_out,
     int n, BoidsParams P, double offset, double cell, int dim, int R, double dt, double blend,
     unsigned long long* __restrict__ pairs)
 {
+    __shared__ int2 runs[RT == 1 ? 9 : 1][128];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     int nnb = 0;
     if (k < n) {
@@ -155,27 +158,47 @@ __global__ void __launch_bounds__(128) boids_rules_kernel(
         double sx = 0, sy = 0, sz = 0, ax = 0, ay = 0, az = 0, hx = 0, hy = 0, hz = 0, cr = 0, cg = 0, cb = 0;
         int nsep = 0;
         const int x0 = max(cx - R, 0), x1 = min(cx + R, dim - 1);
-        for (int ncz = max(cz - R, 0); ncz <= min(cz + R, dim - 1); ++ncz) {
-            for (int ncy = max(cy - R, 0); ncy <= min(cy + R, dim - 1); ++ncy) {
-                const int64_t row = (int64_t)ncy * dim + (int64_t)ncz * dim * dim;
-                const int s = cell_first[row + x0], e = cell_first[row + x1 + 1];   // the row segment is one run
-                for (int j = s; j < e; ++j) {
-                    if (j == k) continue;
-                    const int64_t q = 3 * (int64_t)j;
-                    const double dx = px - pos_in[q], dy = py - pos_in[q + 1], dz = pz - pos_in[q + 2];
-                    const double d2 = dx * dx + dy * dy + dz * dz;
-                    if (d2 < per2 && d2 > 0.0001) {                 // :150
-                        if (d2 < sep2) {                            // :153-158
-                            const double d = sqrt(d2);
-                            const double inv = 1.0 / d;
-                            sx += dx * inv / d; sy += dy * inv / d; sz += dz * inv / d;
-                            ++nsep;
-                        }
-                        ax += vel_in[q]; ay += vel_in[q + 1]; az += vel_in[q + 2];
-                        hx += pos_in[q]; hy += pos_in[q + 1]; hz += pos_in[q + 2];
-                        cr += col_in[q]; cg += col_in[q + 1]; cb += col_in[q + 2];
-                        ++nnb;
+        auto scan_run = [&](int s, int e) {
+            for (int j = s; j < e; ++j) {
+                if (j == k) continue;
+                const int64_t q = 3 * (int64_t)j;
+                const double dx = px - pos_in[q], dy = py - pos_in[q + 1], dz = pz - pos_in[q + 2];
+                const double d2 = dx * dx + dy * dy + dz * dz;
+                if (d2 < per2 && d2 > 0.0001) {                 // :150
+                    if (d2 < sep2) {                            // :153-158
+                        const double d = sqrt(d2);
+                        const double inv = 1.0 / d;
+                        sx += dx * inv / d; sy += dy * inv / d; sz += dz * inv / d;
+                        ++nsep;
                     }
+                    ax += vel_in[q]; ay += vel_in[q + 1]; az += vel_in[q + 2];
+                    hx += pos_in[q]; hy += pos_in[q + 1]; hz += pos_in[q + 2];
+                    cr += col_in[q]; cg += col_in[q + 1]; cb += col_in[q + 2];
+                    ++nnb;
+                }
+            }
+        };
+        if (RT == 1) {
+            // same visiting order as the loops below (z outer, y inner); rows outside the grid are empty runs
+            // (the 18 independent table loads are issued back to back; the runs are parked in shared memory so
+            // the scan stays one compact loop)
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const int ncz = cz - 1 + i / 3, ncy = cy - 1 + i % 3;
+                const bool ok = ncz >= 0 && ncz < dim && ncy >= 0 && ncy < dim;
+                const int64_t row = (int64_t)ncy * dim + (int64_t)ncz * dim * dim;
+                runs[i][threadIdx.x] = ok ? make_int2(cell_first[row + x0], cell_first[row + x1 + 1]) : make_int2(0, 0);
+            }
+#pragma unroll 1
+            for (int i = 0; i < 9; ++i) {
+                const int2 r = runs[i][threadIdx.x];
+                scan_run(r.x, r.y);
+            }
+        } else {
+            for (int ncz = max(cz - R, 0); ncz <= min(cz + R, dim - 1); ++ncz) {
+                for (int ncy = max(cy - R, 0); ncy <= min(cy + R, dim - 1); ++ncy) {
+                    const int64_t row = (int64_t)ncy * dim + (int64_t)ncz * dim * dim;
+                    scan_run(cell_first[row + x0], cell_first[row + x1 + 1]);   // the row segment is one run
                 }
             }
         }
@@ -337,10 +360,16 @@ void boids_step(BoidsSim& s, double dt)
     ++s.launches;
     s.timer.mark(st);
     const double blend = fmin(1.0, s.p.color_blend_rate * dt);   // boids/flock.py:662
-    boids_rules_kernel<<<div_up(n, 128), 128, 0, st>>>(s.pos[o], s.vel[o], s.col[o], s.id[o], s.cell_first,
-                                                       s.pos[s.cur], s.vel[s.cur], s.col[s.cur], s.id[s.cur], n, s.p,
-                                                       s.grid_offset, s.cell_size, s.grid_dim, s.cell_range, dt, blend,
-                                                       s.d_pairs);
+    if (s.cell_range == 1)
+        boids_rules_kernel<1><<<div_up(n, 128), 128, 0, st>>>(s.pos[o], s.vel[o], s.col[o], s.id[o], s.cell_first,
+                                                              s.pos[s.cur], s.vel[s.cur], s.col[s.cur], s.id[s.cur], n, s.p,
+                                                              s.grid_offset, s.cell_size, s.grid_dim, s.cell_range, dt, blend,
+                                                              s.d_pairs);
+    else
+        boids_rules_kernel<0><<<div_up(n, 128), 128, 0, st>>>(s.pos[o], s.vel[o], s.col[o], s.id[o], s.cell_first,
+                                                              s.pos[s.cur], s.vel[s.cur], s.col[s.cur], s.id[s.cur], n, s.p,
+                                                              s.grid_offset, s.cell_size, s.grid_dim, s.cell_range, dt, blend,
+                                                              s.d_pairs);
     ++s.launches;
     B200_CHECK(cudaGetLastError());
     s.timer.mark(st);
