@@ -307,6 +307,8 @@ void boids_alloc(BoidsSim& s, int n)
     s.timer.init();
 }
 
+static void boids_graph_reset(BoidsSim& s);
+
 void boids_free(BoidsSim& s)
 {
     cudaSetDevice(s.device);
@@ -316,6 +318,7 @@ void boids_free(BoidsSim& s)
         cudaFree(s.keys[b]); cudaFree(s.vals[b]);
     }
     s.sorter.destroy();
+    boids_graph_reset(s);
     cudaFree(s.cell_first); cudaFree(s.chunk_lb); cudaFree(s.d_pairs); cudaFree(s.stage);
     s.timer.destroy();
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -337,11 +340,10 @@ void boids_upload(BoidsSim& s, const double* pos, const double* vel, const doubl
     B200_CHECK(cudaStreamSynchronize(s.stream));
 }
 
-void boids_step(BoidsSim& s, double dt)
+// one step's kernels on the stream (captured into a CUDA graph by boids_step)
+static void boids_enqueue(BoidsSim& s, double dt)
 {
-    B200_CHECK(cudaSetDevice(s.device));
     const int n = s.n;
-    if (n == 0) { ++s.steps; return; }
     cudaStream_t st = s.stream;
     const int grid = div_up(n, 256);
     s.timer.begin(st);
@@ -373,6 +375,48 @@ void boids_step(BoidsSim& s, double dt)
     ++s.launches;
     B200_CHECK(cudaGetLastError());
     s.timer.mark(st);
+}
+
+static void boids_graph_reset(BoidsSim& s)
+{
+    if (s.graph_exec) { cudaGraphExecDestroy(s.graph_exec); s.graph_exec = nullptr; }
+}
+
+// The step is ~14 launches and memsets of a few tens of microseconds each: launch-bound.  The same
+// buffers are read and written every step (the rules kernel writes back into the current buffer), so the
+// whole step is captured ONCE into a CUDA graph and replayed; a new dt re-captures (dt and the colour
+// blend are kernel arguments).  Per-phase profiling runs the plain launches.
+void boids_step(BoidsSim& s, double dt)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    if (s.n == 0) { ++s.steps; return; }
+    cudaStream_t st = s.stream;
+    if (s.timer.enabled || !s.use_graph) {
+        boids_enqueue(s, dt);
+    } else {
+        if (!s.graph_exec || s.graph_dt != dt) {
+            boids_graph_reset(s);
+            const int64_t before = s.launches;
+            cudaGraph_t g = nullptr;
+            B200_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            try {
+                boids_enqueue(s, dt);
+            } catch (...) {
+                cudaStreamEndCapture(st, &g);
+                if (g) cudaGraphDestroy(g);
+                throw;
+            }
+            B200_CHECK(cudaStreamEndCapture(st, &g));
+            const cudaError_t e = cudaGraphInstantiate(&s.graph_exec, g, 0);
+            cudaGraphDestroy(g);
+            B200_CHECK(e);
+            s.graph_dt = dt;
+            s.graph_launches = s.launches - before;
+            s.launches = before;
+        }
+        B200_CHECK(cudaGraphLaunch(s.graph_exec, st));
+        s.launches += s.graph_launches;
+    }
     ++s.steps;
     if (s.timer.enabled) {
         B200_CHECK(cudaStreamSynchronize(st));

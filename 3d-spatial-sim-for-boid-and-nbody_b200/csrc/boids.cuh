@@ -49,6 +49,11 @@ struct BoidsSim {
     unsigned long long* d_pairs = nullptr;   // accepted neighbour pairs (device-counted)
     double* stage = nullptr;
 
+    cudaGraphExec_t graph_exec = nullptr;   // the captured step (boids_step)
+    double graph_dt = 0.0;
+    int64_t graph_launches = 0;
+    bool use_graph = true;
+
     PhaseTimer timer;
     int64_t steps = 0;
     int64_t launches = 0;
