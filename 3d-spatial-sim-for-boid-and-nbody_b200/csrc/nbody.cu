@@ -1465,6 +1465,8 @@ void nbody_alloc(NBodySim& s, int n)
     B200_CHECK(cudaFuncSetAttribute(traverse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV_SMEM_BYTES));
     {
         // B200_TRAV = 32 | 64 | t forces a walk; default: chosen per launch (see nbody_traverse)
+        const char* ng = getenv("B200_NO_GRAPH");   // plain launches instead of the captured step (debugging, A/B timing)
+        s.use_graph = !(ng && ng[0] == '1');
         const char* mode = getenv("B200_TRAV");
         s.trav_mode = !mode ? 0 : mode[0] == 't' ? 8 : mode[0] == '6' ? 64 : 32;
     }
@@ -1482,6 +1484,7 @@ void nbody_free(NBodySim& s)
 {
     cudaSetDevice(s.device);
     if (s.stream) cudaStreamSynchronize(s.stream);
+    nbody_graphs_reset(s);
     for (int b = 0; b < 2; ++b) {
         cudaFree(s.pos[b]); cudaFree(s.vel[b]); cudaFree(s.mass[b]); cudaFree(s.id[b]);
         cudaFree(s.keys[b]); cudaFree(s.vals[b]);
@@ -1698,6 +1701,12 @@ void nbody_build_tree_presorted(NBodySim& s)
     build_after_sort(s);
 }
 
+__global__ void init_build_counters_kernel(unsigned* alloc, unsigned* children)
+{
+    *alloc = 1u;
+    *children = 0u;
+}
+
 static void build_after_sort(NBodySim& s)
 {
     const int n = s.n;
@@ -1718,8 +1727,7 @@ static void build_after_sort(NBodySim& s)
     // ---- blocked prefix sums of (m x, m y, m z, m) = node mass / centre of mass; pass 1 of the cell
     // extraction (children lists, pair-block allocation)
     if (n > 1) {
-        B200_CHECK(cudaMemcpyAsync(s.d_alloc, &s.h_one, sizeof(unsigned), cudaMemcpyHostToDevice, st));   // pair 0 is the root's
-        B200_CHECK(cudaMemsetAsync(s.d_children, 0, sizeof(unsigned), st));
+        init_build_counters_kernel<<<1, 1, 0, st>>>(s.d_alloc, s.d_children);   // pair 0 is the root's
         const int nb = div_up(n, PFX_BLOCK);
         const ChildrenArgs ca{s.childL, s.childR, s.parent, s.range, s.lvl, s.meta, s.ishead, s.kids,
                               s.d_alloc, (unsigned)s.rec_capacity, s.d_error, s.d_children};
@@ -1841,10 +1849,90 @@ void nbody_step_end(NBodySim& s, double dt)
     }
 }
 
+// ---------------------------------------------------------------------------- captured step
+// A step is ~25 launches and memsets; below a few hundred thousand bodies it is launch-bound (the
+// reference's own CPU-runnable presets: 10 K - 100 K bodies).  On the handle's own stream the whole step
+// is captured into a CUDA graph and replayed.  The kernel arguments depend on which of the two state
+// buffers is current and on the parameters, so graphs are cached by that key (the buffers alternate:
+// two graphs in steady state); any change (dt, theta, a new state, a shard) captures a new one.
+struct StepGraphKey {
+    int cur, maxabs_slot, shard_begin, shard_end, trav_mode;
+    double dt, G, softening, damping, theta;
+    cudaStream_t stream;
+};
+
+static StepGraphKey step_graph_key(const NBodySim& s, double dt)
+{
+    StepGraphKey k;
+    memset(&k, 0, sizeof(k));
+    k.cur = s.cur; k.maxabs_slot = s.maxabs_slot; k.shard_begin = s.shard_begin; k.shard_end = s.shard_end;
+    k.trav_mode = s.trav_mode;
+    k.dt = dt; k.G = s.G; k.softening = s.softening; k.damping = s.damping; k.theta = s.theta;
+    k.stream = s.stream;
+    return k;
+}
+
+void nbody_graphs_reset(NBodySim& s)
+{
+    for (int i = 0; i < NBodySim::MAX_STEP_GRAPHS; ++i) {
+        if (s.step_graph[i]) cudaGraphExecDestroy(s.step_graph[i]);
+        s.step_graph[i] = nullptr;
+    }
+}
+
 void nbody_step(NBodySim& s, double dt)
 {
-    nbody_step_begin(s);
-    nbody_step_end(s, dt);
+    // (the legacy default stream cannot be captured: a caller that hands in torch's default stream gets plain launches)
+    const bool capturable = s.stream != nullptr && s.stream != cudaStreamLegacy && s.stream != cudaStreamPerThread;
+    const bool plain = s.timer.enabled || s.count_interactions || !capturable || !s.use_graph || s.n < 2;
+    if (plain) {
+        nbody_step_begin(s);
+        nbody_step_end(s, dt);
+        return;
+    }
+    B200_CHECK(cudaSetDevice(s.device));
+    static_assert(sizeof(StepGraphKey) <= sizeof(s.step_graph_key[0]), "graph key storage too small");
+    const StepGraphKey key = step_graph_key(s, dt);
+    int slot = -1;
+    for (int i = 0; i < NBodySim::MAX_STEP_GRAPHS; ++i)
+        if (s.step_graph[i] && memcmp(s.step_graph_key[i], &key, sizeof(key)) == 0) slot = i;
+    const int cur0 = s.cur, mslot0 = s.maxabs_slot;
+    if (slot < 0) {
+        slot = (int)(s.step_graph_next++ % NBodySim::MAX_STEP_GRAPHS);
+        if (s.step_graph[slot]) { cudaGraphExecDestroy(s.step_graph[slot]); s.step_graph[slot] = nullptr; }
+        const int64_t launches0 = s.launches, steps0 = s.steps;
+        cudaGraph_t g = nullptr;
+        B200_CHECK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+        try {
+            nbody_step_begin(s);
+            nbody_step_end(s, dt);
+        } catch (...) {
+            cudaStreamEndCapture(s.stream, &g);
+            if (g) cudaGraphDestroy(g);
+            s.cur = cur0; s.maxabs_slot = mslot0; s.launches = launches0; s.steps = steps0;
+            throw;
+        }
+        B200_CHECK(cudaStreamEndCapture(s.stream, &g));
+        const cudaError_t e = cudaGraphInstantiate(&s.step_graph[slot], g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { s.step_graph[slot] = nullptr; s.cur = cur0; s.maxabs_slot = mslot0; }
+        B200_CHECK(e);
+        memcpy(s.step_graph_key[slot], &key, sizeof(key));
+        s.step_graph_launches[slot] = s.launches - launches0;
+        s.step_graph_sorted_slot[slot] = s.sorted_slot;
+        // the capture ran the host side of the step (buffer flips, counters); undo the counters, keep the flips
+        s.launches = launches0;
+        s.steps = steps0;
+    } else {
+        // replay: the host-side effects of the step
+        s.cur = cur0 ^ 1;
+        s.maxabs_slot = mslot0 ^ 1;
+        s.sorted_slot = s.step_graph_sorted_slot[slot];
+    }
+    B200_CHECK(cudaGraphLaunch(s.step_graph[slot], s.stream));
+    s.launches += s.step_graph_launches[slot];
+    ++s.steps;
+    s.tree_valid = false;
 }
 
 // ---------------------------------------------------------------------------- FP32 peak probe

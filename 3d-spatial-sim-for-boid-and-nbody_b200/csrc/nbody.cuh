@@ -80,7 +80,6 @@ struct NBodySim {
     int* d_root = nullptr;
     unsigned* d_alloc = nullptr;              // pair-record allocator
     unsigned* d_children = nullptr;           // octree children (cells + leaves) of the last tree
-    unsigned h_one = 1u;
     unsigned* d_tile_counter = nullptr;
     unsigned long long* d_interactions = nullptr;
     unsigned* d_error = nullptr;
@@ -88,6 +87,14 @@ struct NBodySim {
     float* colors = nullptr;                  // (N,3) f32, creation order
     void* stage = nullptr;                    // (N,3) f64-sized staging for getters
     bool tree_valid = false;                  // keys/perm/tree describe the current positions
+    // captured steps (nbody_step): CUDA graphs cached by (current buffer, parameters)
+    static constexpr int MAX_STEP_GRAPHS = 4;
+    cudaGraphExec_t step_graph[MAX_STEP_GRAPHS] = {nullptr, nullptr, nullptr, nullptr};
+    alignas(8) unsigned char step_graph_key[MAX_STEP_GRAPHS][80] = {};
+    int64_t step_graph_launches[MAX_STEP_GRAPHS] = {0, 0, 0, 0};
+    int step_graph_sorted_slot[MAX_STEP_GRAPHS] = {0, 0, 0, 0};
+    unsigned step_graph_next = 0;
+    bool use_graph = true;
     int trav_mode = 0;                        // 0: per launch (64 for large N and theta, else 32); 32 / 64: forced; 8: experimental transposed walk
     bool count_interactions = false;          // exact per-body interaction counts in the traversal (slower)
 
@@ -132,6 +139,7 @@ void nbody_ms_sort_local(NBodySim& s, int rank);
 void nbody_build_tree_presorted(NBodySim& s);
 void nbody_integrate(NBodySim& s, double dt);
 void nbody_step(NBodySim& s, double dt);
+void nbody_graphs_reset(NBodySim& s);
 // split step for sharded runs: begin = tree + traversal of [shard_begin, shard_end); the caller
 // then exchanges acc slices between ranks on the same stream; end = integrate of all bodies.
 void nbody_step_begin(NBodySim& s);

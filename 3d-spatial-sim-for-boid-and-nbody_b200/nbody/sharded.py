@@ -83,6 +83,10 @@ class ShardedSimulation:
             self.vals_all = torch.as_tensor(_DeviceArray(vp, (self.S * world, 1), "<i4"), device=dev)
 
     def step(self, dt: float):
+        if self.world == 1:      # nothing to exchange: the library's captured step (CUDA graph)
+            self.sim.step(dt)
+            self._in_morton_order = True
+            return
         if self.sharded_sort and self._in_morton_order:
             self.sim.sort_local(self.rank)
             all_gather_slices(self.keys_all, self.rank, self.world, self.group)

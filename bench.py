@@ -410,6 +410,9 @@ def run_gpu(args):
     else:
         torch.cuda.set_device(0)
         local = 0
+    # everything (kernels, collectives, timing events) on one non-default stream: the library captures its
+    # step into a CUDA graph, which the legacy default stream does not allow
+    torch.cuda.set_stream(torch.cuda.Stream())
     import b200sim
     from b200sim import _lib
     _lib.load()   # fails loudly if the CUDA library is missing

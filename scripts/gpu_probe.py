@@ -1,4 +1,5 @@
 """Quick per-phase timing probe of the n-body step (development aid)."""
+import os
 import sys
 import time
 
@@ -52,3 +53,11 @@ if "--nocount" not in sys.argv:
               "pair evals/batch", st["trav_pair_slots"] / st["trav_batches"], "stack max", st["trav_stack_max"],
               "shared fraction of evals", 2 * st.get("trav_shared_pairs", 0) / st["trav_pair_slots"])
     print("traversal TFLOP/s (20 flop/interaction)", 20 * ips / tr / 1e12)
+for _ in range(3):
+    sim.step(cfg["dt"])
+sim.sync()
+t0 = time.time()
+for _ in range(steps):
+    sim.step(cfg["dt"])
+sim.sync()
+print("unprofiled wall ms/step", 1e3 * (time.time() - t0) / steps, "(captured step)")
