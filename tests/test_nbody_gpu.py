@@ -361,6 +361,36 @@ def test_async_frame_and_state_prefetch_match_blocking_calls():
         b.set_state_commit()                       # nothing pending
 
 
+def test_captured_step_is_bit_identical_to_plain_launches(monkeypatch):
+    """step() replays CUDA graphs cached by (state buffer, parameters); the plain launches
+    (B200_NO_GRAPH=1) must give the same bits through dt changes, a new state and a parameter change."""
+    from b200sim import presets
+    n = 30_000
+    pos, vel, mass = presets.generate("collision", n, 300.0, 0.1, 4)
+
+    def run():
+        sim = _sim(pos, vel, mass, 0.1, 1.5, theta=0.7)
+        for dt in (0.05, 0.05, 0.05, 0.02, 0.05, 0.05):
+            sim.step(dt)
+        sim.set_state(pos * 1.01, vel)
+        for _ in range(3):
+            sim.step(0.05)
+        sim.set_params(0.1, 1.5, 0.999, 0.5)
+        for _ in range(9):          # more distinct keys than cached graphs
+            sim.step(0.03)
+        sim.step_n(0.03, 3)
+        out = (sim.get_positions_f64(), sim.get_velocities(), sim.get_stats()["steps"], sim.launch_count())
+        sim.close()
+        return out
+
+    monkeypatch.setenv("B200_NO_GRAPH", "1")
+    p0, v0, s0, l0 = run()
+    monkeypatch.setenv("B200_NO_GRAPH", "0")
+    p1, v1, s1, l1 = run()
+    assert np.array_equal(p0, p1) and np.array_equal(v0, v1)
+    assert s0 == s1 == 21 and l0 == l1
+
+
 def test_device_delta_frames_are_the_recorders_format2_payload(tmp_path):
     """Frame codec: int16 deltas produced on the device equal the recorder's host
     arithmetic int16((frame - prev) * 1000) on the float32 frames (tools/record.py:256-262), bit for
