@@ -791,6 +791,13 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 4) traverse_kernel(const float4* _
 // has its own loop, so a half never evaluates a pair none of its lanes asked for: the evaluated
 // (pair, half) set is exactly that of two independent 32-body walks, every lane still makes the
 // reference's per-body MAC decision.
+#ifndef TRAV64_UNROLL_BOTH
+#define TRAV64_UNROLL_BOTH 2
+#endif
+#ifndef TRAV64_UNROLL_ONE
+#define TRAV64_UNROLL_ONE 4
+#endif
+constexpr int U64_BOTH = TRAV64_UNROLL_BOTH, U64_ONE = TRAV64_UNROLL_ONE;   // eval loop unroll factors
 struct __align__(16) WarpShared64 {
     unsigned stk_first[TRAV_CAP];        // pair index | (pairs - 1) << 29 (one pair, except chunks of a bucket)
     unsigned stk_lo[TRAV_CAP];           // lanes whose body l opened the pair's parent cell
@@ -919,7 +926,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 3) traverse64_kernel(const float4*
             __syncwarp();
             // ---- eval, one loop per class
             const int jL = nB + nL;
-#pragma unroll 2
+#pragma unroll U64_BOTH
             for (int j = 0; j < nB; ++j) {
                 const float4 XY = sXY[j];
                 const float4 ZM = sZM[j];
@@ -929,7 +936,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 3) traverse64_kernel(const float4*
                 eval_pair<COUNT>(XY, ZM, TM.x, TM.y, __float_as_uint(TM.w), lanebit, eps22, B, om.z, om.w);
                 if (lane == 0) sOP[j] = om;
             }
-#pragma unroll 4
+#pragma unroll U64_ONE
             for (int j = nB; j < jL; ++j) {
                 const float4 XY = sXY[j];
                 const float4 ZM = sZM[j];
@@ -938,7 +945,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 3) traverse64_kernel(const float4*
                 eval_pair<COUNT>(XY, ZM, TM.x, TM.y, __float_as_uint(TM.z), lanebit, eps22, A, om.x, om.y);
                 if (lane == 0) sOP[j] = om;
             }
-#pragma unroll 4
+#pragma unroll U64_ONE
             for (int j = jL; j < P; ++j) {
                 const float4 XY = sXY[j];
                 const float4 ZM = sZM[j];
