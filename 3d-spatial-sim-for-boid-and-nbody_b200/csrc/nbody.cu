@@ -2090,7 +2090,7 @@ static void async_free(NBodySim& s)
     cudaStreamSynchronize(s.up_stream);
     cudaStreamSynchronize(s.down_stream);
     cudaFree(s.frame_pos); cudaFree(s.frame_col); cudaFree(s.up_pos); cudaFree(s.up_vel);
-    if (s.frame_dpos) { cudaFree(s.frame_dpos); cudaFree(s.frame_dcol); s.frame_dpos = s.frame_dcol = nullptr; }
+    if (s.frame_dpos) { cudaFree(s.frame_dpos); cudaFree(s.frame_dcol); cudaFree(s.frame_pos2); cudaFree(s.frame_col2); s.frame_dpos = s.frame_dcol = nullptr; }
     cudaEventDestroy(s.ev_frame_ready); cudaEventDestroy(s.ev_frame_done);
     cudaEventDestroy(s.ev_upload_done); cudaEventDestroy(s.ev_upload_consumed);
     cudaStreamDestroy(s.up_stream); cudaStreamDestroy(s.down_stream);
@@ -2154,24 +2154,23 @@ __device__ __forceinline__ short delta_i16(float cur, float prev)
     return (short)(unsigned short)((unsigned)v & 0xffffu);
 }
 
-__global__ void __launch_bounds__(256) frame_delta_kernel(const double* __restrict__ pos, const double* __restrict__ vel,
-                                                          const uint32_t* __restrict__ id, float* __restrict__ fpos,
-                                                          float* __restrict__ fcol, short* __restrict__ dpos,
-                                                          short* __restrict__ dcol, int n, double max_speed)
+// Elementwise over the two creation-order float32 frames (fully coalesced; the random un-permute is done
+// once, by frame_kernel, into the other staging buffer).  count = 3 n components, two per thread.
+__global__ void __launch_bounds__(256) frame_delta_kernel(const float2* __restrict__ cur_pos, const float2* __restrict__ prev_pos,
+                                                          const float2* __restrict__ cur_col, const float2* __restrict__ prev_col,
+                                                          short2* __restrict__ dpos, short2* __restrict__ dcol, int64_t pairs,
+                                                          int64_t count)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const int64_t o = 3 * (int64_t)k, w = 3 * (int64_t)id[k];
-    const double vx = vel[o], vy = vel[o + 1], vz = vel[o + 2];
-    float c[3];
-    speed_color(fmin(1.0, sqrt(vx * vx + vy * vy + vz * vz) / max_speed), c[0], c[1], c[2]);
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const float p = (float)pos[o + a];
-        dpos[w + a] = delta_i16(p, fpos[w + a]);
-        dcol[w + a] = delta_i16(c[a], fcol[w + a]);
-        fpos[w + a] = p;
-        fcol[w + a] = c[a];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pairs) {
+        const float2 a = cur_pos[i], b = prev_pos[i], c = cur_col[i], d = prev_col[i];
+        dpos[i] = make_short2(delta_i16(a.x, b.x), delta_i16(a.y, b.y));
+        dcol[i] = make_short2(delta_i16(c.x, d.x), delta_i16(c.y, d.y));
+    } else if (i == pairs && (count & 1)) {   // odd tail component
+        const float* cp = reinterpret_cast<const float*>(cur_pos); const float* pp = reinterpret_cast<const float*>(prev_pos);
+        const float* cc = reinterpret_cast<const float*>(cur_col); const float* pc = reinterpret_cast<const float*>(prev_col);
+        reinterpret_cast<short*>(dpos)[count - 1] = delta_i16(cp[count - 1], pp[count - 1]);
+        reinterpret_cast<short*>(dcol)[count - 1] = delta_i16(cc[count - 1], pc[count - 1]);
     }
 }
 
@@ -2181,15 +2180,26 @@ void nbody_frame_delta_begin(NBodySim& s, double max_speed, short* host_dpos, sh
     if (s.n == 0) return;
     B200_REQUIRE(s.frame_has_prev, "frame_delta_begin needs a previous frame (call frame_begin first)");
     const size_t N = (size_t)s.n;
-    if (!s.frame_dpos) {
+    if (!s.frame_dpos) {   // second float32 staging (the frames alternate between the two) + the int16 payloads
+        s.frame_pos2 = alloc_counted<float>(s, 3 * N);
+        s.frame_col2 = alloc_counted<float>(s, 3 * N);
         s.frame_dpos = alloc_counted<short>(s, 3 * N);
         s.frame_dcol = alloc_counted<short>(s, 3 * N);
     }
     if (s.frame_pending) B200_CHECK(cudaStreamWaitEvent(s.stream, s.ev_frame_done, 0));   // staging still being read
-    frame_delta_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.pos[s.cur], s.vel[s.cur], s.id[s.cur], s.frame_pos, s.frame_col,
-                                                               s.frame_dpos, s.frame_dcol, s.n, max_speed);
-    ++s.launches;
+    float* prev_pos = s.frame_pos; float* prev_col = s.frame_col;
+    float* cur_pos = s.frame_pos2; float* cur_col = s.frame_col2;
+    frame_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.pos[s.cur], s.vel[s.cur], s.id[s.cur], cur_pos, cur_col, s.n, max_speed);
+    const int64_t count = 3 * (int64_t)N, pairs = count / 2;
+    frame_delta_kernel<<<(unsigned)((pairs + 1 + 255) / 256), 256, 0, s.stream>>>(
+        reinterpret_cast<const float2*>(cur_pos), reinterpret_cast<const float2*>(prev_pos),
+        reinterpret_cast<const float2*>(cur_col), reinterpret_cast<const float2*>(prev_col),
+        reinterpret_cast<short2*>(s.frame_dpos), reinterpret_cast<short2*>(s.frame_dcol), pairs, count);
+    s.launches += 2;
     B200_CHECK(cudaGetLastError());
+    // the new frame becomes the "previous frame" (and the staging frame_begin writes to)
+    s.frame_pos = cur_pos; s.frame_col = cur_col;
+    s.frame_pos2 = prev_pos; s.frame_col2 = prev_col;
     B200_CHECK(cudaEventRecord(s.ev_frame_ready, s.stream));
     B200_CHECK(cudaStreamWaitEvent(s.down_stream, s.ev_frame_ready, 0));
     B200_CHECK(cudaMemcpyAsync(host_dpos, s.frame_dpos, 3 * N * sizeof(short), cudaMemcpyDeviceToHost, s.down_stream));
