@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libb200sim.so")
 SOURCES = ["nbody.cu", "boids.cu", "capi.cu"]
-HEADERS = ["common.cuh", "radix_sort.cuh", "nbody.cuh", "boids.cuh",
+HEADERS = ["common.cuh", "radix_sort.cuh", "nbody.cuh", "traverse.cuh", "boids.cuh",
            os.path.join("..", "..", "include", "b200sim.h")]
 
 NVCC_FLAGS = [

@@ -1,0 +1,758 @@
+// traverse.cuh -- theta-MAC force traversal kernels of the Barnes-Hut step (included by nbody.cu, inside
+// namespace b200, after the pair-record definitions it reads).  See DESIGN.md section 4.
+#pragma once
+
+// ============================================================================ traversal
+// One warp owns 32 consecutive sorted bodies (one per lane) and walks the octree for all of them
+// at once.  Work is organised in BATCHES so that the tree-walk bookkeeping is done by 32 lanes in
+// parallel and the inner loop is nothing but arithmetic:
+//   select  pop as many entries (cell's child block, pair count, lane mask) from the warp's stack
+//           as fit 32 pair slots (one lane per entry + a warp prefix sum)
+//   load    the pair records of all selected cells: coalesced 16 B/lane loads, staged in shared
+//           memory as SoA {x0,x1,y0,y1} {z0,z1,m0,m1} {T0,T1,mask} {first0,first1,n0,n1}
+//   eval    every lane evaluates every staged pair, TWO children per iteration with Blackwell's
+//           packed fp32x2 instructions (FADD2/FMUL2/FFMA2, sm_100+) from shared-memory broadcasts:
+//             d2 = |com - p|^2 + eps^2;   open iff d2 <= T;   otherwise a += m (com - p) d2^-3/2
+//           lane 0 records the two ballots of "open" per pair
+//   expand  lane j turns pair j's ballots into new stack entries (cells with children that some
+//           lane must open, with the mask of exactly those lanes) -- a ballot/popc prefix sum
+// T = max(size^2/theta^2, eps^2) (leaf: eps^2).  This is the reference's "accept iff
+// size/d < theta, add iff d^2 > eps^2" (nbody/simulation.py:252-267): for size^2/theta^2 >= eps^2
+// the tests coincide; otherwise the cell is always accepted and only d2 == eps^2 (zero distance:
+// the body itself) is excluded -- it "opens" nothing because leaves have no children.
+// Every lane makes the reference's own per-body MAC decision; there is no group MAC.  Lanes
+// outside a pair's mask take x = 1e18: d2 ~ 1e36 > T, so they never open, and their
+// "contribution" m * d2^-3/2 underflows to exactly 0; no per-child mask logic is needed.
+// The stack is depth-first in batches: while it holds more than TRAV_DFS_MARK entries only the
+// top entry is popped per batch, which bounds it by MARK + 64 + 7 * 21 < TRAV_CAP.
+struct __align__(16) WarpShared {
+    unsigned stk_first[TRAV_CAP];        // first pair of the child block | (pairs - 1) << 29
+    unsigned stk_mask[TRAV_CAP];         // lanes that must open the cell
+    // XY[32] ZM[32] TM[32] FN[32] OP[32]; areas are TRAV_AREA = 34 entries apart so that the four
+    // 16-byte quarters of a pair record, stored by four neighbouring lanes, fall in different banks
+    float4 stage[5 * TRAV_AREA];
+    unsigned d_first[TRAV_BATCH];        // pair slot -> global pair index
+    unsigned d_mask[TRAV_BATCH];         //           -> lane mask
+};
+static_assert(sizeof(WarpShared) % 16 == 0, "WarpShared must keep float4 alignment");
+constexpr size_t TRAV_SMEM_BYTES = sizeof(WarpShared) * TRAV_WARPS;
+constexpr unsigned TRAV_FIRST_MASK = (1u << 29) - 1u;
+constexpr int TRAV_CHUNK_PAIRS = 8;      // an entry holds <= 8 pairs (3 bits); larger buckets are split
+
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// The MAC of both children of a pair for one lane: a lane inside the pair's mask accepts a child iff
+// d2 > T (one FSETP with the mask bit as its predicate operand); r = accept ? d2^-1/2 : 0.  The
+// ballots are of "not accepted" and still contain the lanes outside the mask: expand() removes them.
+__device__ __forceinline__ void mac_pair(float2 d2, float T0, float T1, bool in, unsigned& om0, unsigned& om1, float2& r)
+{
+    const bool a0 = in && d2.x > T0, a1 = in && d2.y > T1;
+    om0 = __ballot_sync(0xffffffffu, !a0);
+    om1 = __ballot_sync(0xffffffffu, !a1);
+    r.x = a0 ? rsqrt_approx(d2.x) : 0.f;
+    r.y = a1 ? rsqrt_approx(d2.y) : 0.f;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRAV_BLOCK, 4) traverse_kernel(const float4* __restrict__ recs, const float4* __restrict__ posm,
+                                                                 float4* __restrict__ acc, int tile_begin, int tile_end, int n,
+                                                                 float eps2, float G, unsigned* tile_counter,
+                                                                 unsigned long long* counters, unsigned* error)
+{
+    extern __shared__ __align__(16) unsigned char trav_smem[];
+    const unsigned lane = lane_id();
+    const unsigned lanebit = 1u << lane;
+    const unsigned lt = lanemask_lt();
+    WarpShared& ws = reinterpret_cast<WarpShared*>(trav_smem)[threadIdx.x >> 5];
+    const float4* sXY = ws.stage;
+    const float4* sZM = ws.stage + TRAV_AREA;
+    const float4* sTM = ws.stage + 2 * TRAV_AREA;
+    const float4* sFN = ws.stage + 3 * TRAV_AREA;
+    uint4* sOP = reinterpret_cast<uint4*>(ws.stage + 4 * TRAV_AREA);   // .x/.y = ballots of "open", child 0 / 1
+    const float2 eps22 = make_float2(eps2, eps2);
+    unsigned long long w_inter = 0, w_slots = 0, w_lanepairs = 0, w_batches = 0;
+    int w_spmax = 0;
+
+    for (;;) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        const int tile = tile_begin + (int)t;
+        if (tile >= tile_end) break;
+        const int k = tile * 32 + (int)lane;
+        const bool valid = k < n;
+        const float4 p = valid ? posm[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float2 npx = make_float2(-p.x, -p.x), npy = make_float2(-p.y, -p.y), npz = make_float2(-p.z, -p.z);
+        float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;   // (even, odd) children accumulate separately
+        int cnt = 0, lanepairs = 0, slots = 0;
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) { ws.stk_first[0] = 0u; ws.stk_mask[0] = vmask; }   // pair 0 = {root, dummy}
+        int sp = 1;
+        __syncwarp();
+        while (sp > 0) {
+            // ---- select: lane l looks at the l-th entry from the top
+            const int idx = sp - 1 - (int)lane;
+            unsigned ef = 0, em = 0;
+            int np = 0;
+            if (idx >= 0) { ef = ws.stk_first[idx]; em = ws.stk_mask[idx]; np = (int)(ef >> 29) + 1; }
+            int incl = np;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += u;
+            }
+            const int limit = sp > TRAV_DFS_MARK ? 1 : 32;
+            const bool take = idx >= 0 && incl <= TRAV_BATCH && (int)lane < limit;
+            const int E = __popc(__ballot_sync(0xffffffffu, take));   // take is a prefix of the lanes; E >= 1
+            // (the max-reduce leaves P in a uniform register: the loops below are provably convergent)
+            const int P = __reduce_max_sync(0xffffffffu, (int)lane == E - 1 ? incl : 0);
+            sp -= E;
+            if ((int)lane < E) {
+                const int base = incl - np;
+                const unsigned f = ef & TRAV_FIRST_MASK;
+                for (int q = 0; q < np; ++q) { ws.d_first[base + q] = f + q; ws.d_mask[base + q] = em; }
+            }
+            __syncwarp();
+            // ---- load: 8 pair records (4 x 16 B each) per warp-wide load
+#pragma unroll
+            for (int it = 0; it < TRAV_BATCH / 8; ++it) {
+                const int slot = it * 8 + (int)(lane >> 2);
+                if (slot < P) {
+                    float4 v = __ldg(&recs[4 * (int64_t)ws.d_first[slot] + (lane & 3u)]);
+                    if ((lane & 3u) == 2u) v.z = __uint_as_float(ws.d_mask[slot]);
+                    ws.stage[(lane & 3u) * TRAV_AREA + slot] = v;
+                }
+            }
+            __syncwarp();
+            // ---- eval
+#pragma unroll 4
+            for (int j = 0; j < P; ++j) {
+                const float4 XY = sXY[j];
+                const float4 ZM = sZM[j];
+                const float4 TM = sTM[j];
+                const bool inbit = (__float_as_uint(TM.z) & lanebit) != 0u;
+                const float2 dx = __fadd2_rn(make_float2(XY.x, XY.y), npx);
+                const float2 dy = __fadd2_rn(make_float2(XY.z, XY.w), npy);
+                const float2 dz = __fadd2_rn(make_float2(ZM.x, ZM.y), npz);
+                const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, eps22)));
+                unsigned om0, om1;
+                float2 r;
+                mac_pair(d2, TM.x, TM.y, inbit, om0, om1, r);
+                if (lane == 0) *reinterpret_cast<uint2*>(&sOP[j]) = make_uint2(om0, om1);
+                if (COUNT) {
+                    if (inbit) {
+                        ++lanepairs;
+                        if (r.x != 0.f && XY.x < 2e18f) ++cnt;
+                        if (r.y != 0.f && XY.y < 2e18f) ++cnt;
+                    }
+                }
+                const float2 f = __fmul2_rn(make_float2(ZM.z, ZM.w), __fmul2_rn(__fmul2_rn(r, r), r));
+                ax = __ffma2_rn(dx, f, ax);
+                ay = __ffma2_rn(dy, f, ay);
+                az = __ffma2_rn(dz, f, az);
+            }
+            slots += P;
+            __syncwarp();
+            // ---- expand: lane j owns pair slot j
+            bool c0 = false, c1 = false;
+            unsigned f0 = 0, f1 = 0, n0 = 0, n1 = 0;
+            uint2 om = make_uint2(0u, 0u);
+            if ((int)lane < P) {
+                om = *reinterpret_cast<const uint2*>(&sOP[lane]);
+                const unsigned mask = __float_as_uint(sTM[lane].z);   // the ballots include the lanes outside the mask
+                om.x &= mask; om.y &= mask;
+                const float4 fn = sFN[lane];
+                f0 = __float_as_uint(fn.x); f1 = __float_as_uint(fn.y);
+                n0 = __float_as_uint(fn.z); n1 = __float_as_uint(fn.w);
+                c0 = om.x != 0u && n0 != 0u;
+                c1 = om.y != 0u && n1 != 0u;
+            }
+            const int np0 = (int)((n0 + 1u) >> 1), np1 = (int)((n1 + 1u) >> 1);
+            const bool big = (c0 && np0 > TRAV_CHUNK_PAIRS) || (c1 && np1 > TRAV_CHUNK_PAIRS);
+            if (!__any_sync(0xffffffffu, big)) {
+                const unsigned b0 = __ballot_sync(0xffffffffu, c0), b1 = __ballot_sync(0xffffffffu, c1);
+                int pos = sp + __popc(b0 & lt) + __popc(b1 & lt);
+                if (c0) { ws.stk_first[pos] = f0 | ((unsigned)(np0 - 1) << 29); ws.stk_mask[pos] = om.x; ++pos; }
+                if (c1) { ws.stk_first[pos] = f1 | ((unsigned)(np1 - 1) << 29); ws.stk_mask[pos] = om.y; }
+                sp += __popc(b0) + __popc(b1);
+            } else {
+                // rare: a bucket of > 16 bodies sharing one finest-level cell is pushed in chunks
+                const int e0 = c0 ? (np0 + TRAV_CHUNK_PAIRS - 1) / TRAV_CHUNK_PAIRS : 0;
+                const int e1 = c1 ? (np1 + TRAV_CHUNK_PAIRS - 1) / TRAV_CHUNK_PAIRS : 0;
+                int inc2 = e0 + e1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, inc2, o);
+                    if ((int)lane >= o) inc2 += u;
+                }
+                const int total = __shfl_sync(0xffffffffu, inc2, 31);
+                if (sp + total > TRAV_CAP) {   // never drop silently
+                    if (lane == 0) atomicOr(error, (unsigned)ERR_STACK_OVERFLOW);
+                    sp = 0;
+                } else {
+                    int pos = sp + inc2 - (e0 + e1);
+                    for (int q = 0; q < e0; ++q, ++pos) {
+                        const int r = min(np0 - TRAV_CHUNK_PAIRS * q, TRAV_CHUNK_PAIRS);
+                        ws.stk_first[pos] = (f0 + (unsigned)(TRAV_CHUNK_PAIRS * q)) | ((unsigned)(r - 1) << 29);
+                        ws.stk_mask[pos] = om.x;
+                    }
+                    for (int q = 0; q < e1; ++q, ++pos) {
+                        const int r = min(np1 - TRAV_CHUNK_PAIRS * q, TRAV_CHUNK_PAIRS);
+                        ws.stk_first[pos] = (f1 + (unsigned)(TRAV_CHUNK_PAIRS * q)) | ((unsigned)(r - 1) << 29);
+                        ws.stk_mask[pos] = om.y;
+                    }
+                    sp += total;
+                }
+            }
+            if (COUNT) { ++w_batches; w_spmax = max(w_spmax, sp); }
+            __syncwarp();
+        }
+        // acc.w: exact interaction count (COUNT) or the tile's evaluated pair slots (a cost proxy)
+        if (valid) acc[k] = make_float4(G * (ax.x + ax.y), G * (ay.x + ay.y), G * (az.x + az.y), __int_as_float(COUNT ? cnt : slots));
+        if (COUNT) {
+            unsigned c32 = valid ? (unsigned)cnt : 0u, l32 = (unsigned)lanepairs;
+            for (int o = 16; o > 0; o >>= 1) {
+                c32 += __shfl_xor_sync(0xffffffffu, c32, o);
+                l32 += __shfl_xor_sync(0xffffffffu, l32, o);
+            }
+            w_inter += c32;
+            w_lanepairs += l32;
+            w_slots += (unsigned)slots;
+        }
+    }
+    if (COUNT && lane == 0) {
+        if (w_inter) atomicAdd(&counters[0], w_inter);
+        atomicAdd(&counters[1], w_slots);
+        atomicAdd(&counters[2], w_lanepairs);
+        atomicAdd(&counters[3], w_batches);
+        atomicMax(&counters[4], (unsigned long long)w_spmax);
+    }
+}
+
+// ---------------------------------------------------------------------------- 64-body walk
+// The same walk with TWO bodies per lane: a warp owns 64 consecutive sorted bodies (lane l: bodies l
+// and l + 32 of the tile), a stack entry carries one lane mask per 32-body half.  A staged pair
+// record is read from shared memory once for both halves and the batch bookkeeping is shared, which
+// halves the shared-memory wavefronts and the walk overhead per evaluated pair.  A batch is sorted by
+// class -- pairs needed by both halves, only by the low half, only by the high half -- and each class
+// has its own loop, so a half never evaluates a pair none of its lanes asked for: the evaluated
+// (pair, half) set is exactly that of two independent 32-body walks, every lane still makes the
+// reference's per-body MAC decision.
+#ifndef TRAV64_UNROLL_BOTH
+#define TRAV64_UNROLL_BOTH 2
+#endif
+#ifndef TRAV64_UNROLL_ONE
+#define TRAV64_UNROLL_ONE 4
+#endif
+constexpr int U64_BOTH = TRAV64_UNROLL_BOTH, U64_ONE = TRAV64_UNROLL_ONE;   // eval loop unroll factors
+struct __align__(16) WarpShared64 {
+    unsigned stk_first[TRAV_CAP];        // pair index | (pairs - 1) << 29 (one pair, except chunks of a bucket)
+    unsigned stk_lo[TRAV_CAP];           // lanes whose body l opened the pair's parent cell
+    unsigned stk_hi[TRAV_CAP];           //                 body l + 32
+    float4 stage[5 * TRAV_AREA];         // XY ZM {T0,T1,mask lo,mask hi} FN {open lo 0, lo 1, hi 0, hi 1}
+};
+constexpr size_t TRAV64_SMEM_BYTES = sizeof(WarpShared64) * TRAV_WARPS;
+
+struct EvalBody {
+    float npx, npy, npz;                 // -position
+    float2 ax, ay, az;                   // (even, odd) children accumulate separately
+    int cnt, lanepairs;
+};
+
+template <bool COUNT>
+__device__ __forceinline__ void eval_pair(const float4& XY, const float4& ZM, float T0, float T1, unsigned mask, unsigned lanebit,
+                                          float2 eps22, EvalBody& b, unsigned& om0, unsigned& om1)
+{
+    const bool inbit = (mask & lanebit) != 0u;
+    const float2 dx = __fadd2_rn(make_float2(XY.x, XY.y), make_float2(b.npx, b.npx));
+    const float2 dy = __fadd2_rn(make_float2(XY.z, XY.w), make_float2(b.npy, b.npy));
+    const float2 dz = __fadd2_rn(make_float2(ZM.x, ZM.y), make_float2(b.npz, b.npz));
+    const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, eps22)));
+    float2 r;
+    mac_pair(d2, T0, T1, inbit, om0, om1, r);
+    if (COUNT) {
+        if (inbit) {
+            ++b.lanepairs;
+            if (r.x != 0.f && XY.x < 2e18f) ++b.cnt;
+            if (r.y != 0.f && XY.y < 2e18f) ++b.cnt;
+        }
+    }
+    const float2 f = __fmul2_rn(make_float2(ZM.z, ZM.w), __fmul2_rn(__fmul2_rn(r, r), r));
+    b.ax = __ffma2_rn(dx, f, b.ax);
+    b.ay = __ffma2_rn(dy, f, b.ay);
+    b.az = __ffma2_rn(dz, f, b.az);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRAV_BLOCK, 3) traverse64_kernel(const float4* __restrict__ recs, const float4* __restrict__ posm,
+                                                                   float4* __restrict__ acc, int begin, int end,
+                                                                   float eps2, float G, unsigned* tile_counter,
+                                                                   unsigned long long* counters, unsigned* error)
+{
+    extern __shared__ __align__(16) unsigned char trav_smem[];
+    const unsigned lane = lane_id();
+    const unsigned lanebit = 1u << lane;
+    const unsigned lt = lanemask_lt();
+    WarpShared64& ws = reinterpret_cast<WarpShared64*>(trav_smem)[threadIdx.x >> 5];
+    const float4* sXY = ws.stage;
+    const float4* sZM = ws.stage + TRAV_AREA;
+    const float4* sTM = ws.stage + 2 * TRAV_AREA;
+    const float4* sFN = ws.stage + 3 * TRAV_AREA;
+    uint4* sOP = reinterpret_cast<uint4*>(ws.stage + 4 * TRAV_AREA);
+    const float2 eps22 = make_float2(eps2, eps2);
+    unsigned long long w_inter = 0, w_slots = 0, w_lanepairs = 0, w_batches = 0, w_both = 0;
+    int w_spmax = 0;
+
+    for (;;) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1u);
+        t = __reduce_max_sync(0xffffffffu, t);   // (broadcast through a uniform register: the compiler can prove the walk convergent)
+        const int64_t base = (int64_t)begin + 64 * (int64_t)t;
+        if (base >= end) break;
+        const int ka = (int)base + (int)lane, kb = ka + 32;
+        const bool va = ka < end, vb = kb < end;
+        EvalBody A, B;
+        {
+            const float4 pa = va ? posm[ka] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 pb = vb ? posm[kb] : make_float4(0.f, 0.f, 0.f, 0.f);
+            A.npx = -pa.x; A.npy = -pa.y; A.npz = -pa.z;
+            B.npx = -pb.x; B.npy = -pb.y; B.npz = -pb.z;
+        }
+        A.ax = A.ay = A.az = B.ax = B.ay = B.az = make_float2(0.f, 0.f);
+        A.cnt = A.lanepairs = B.cnt = B.lanepairs = 0;
+        int slots_a = 0, slots_b = 0;
+        {
+            const unsigned vma = __ballot_sync(0xffffffffu, va), vmb = __ballot_sync(0xffffffffu, vb);
+            if (lane == 0) { ws.stk_first[0] = 0u; ws.stk_lo[0] = vma; ws.stk_hi[0] = vmb; }   // pair 0 = {root, dummy}
+        }
+        int sp = 1;
+        __syncwarp();
+        while (sp > 0) {
+            // ---- select: the top entries, one per lane, sorted by class (both | low only | high only)
+            const int idx = sp - 1 - (int)lane;
+            unsigned ef = 0, ml = 0, mh = 0;
+            if (idx >= 0) { ef = ws.stk_first[idx]; ml = ws.stk_lo[idx]; mh = ws.stk_hi[idx]; }
+            const unsigned multi = __ballot_sync(0xffffffffu, (ef >> 29) != 0u);
+            const bool chunk = (multi & 1u) != 0u;
+            const unsigned ef0 = __shfl_sync(0xffffffffu, ef, 0);
+            const unsigned ml0 = __shfl_sync(0xffffffffu, ml, 0), mh0 = __shfl_sync(0xffffffffu, mh, 0);
+            const int room = (TRAV_CAP - TRAV_RESERVE - sp) / 7;
+            int E = min(min(sp, TRAV_BATCH), max(room, 1));
+            if (multi) E = min(E, __ffs(multi) - 1);
+            const bool taken = (int)lane < E;
+            const unsigned bB = __ballot_sync(0xffffffffu, taken && ml != 0u && mh != 0u);
+            const unsigned bL = __ballot_sync(0xffffffffu, taken && mh == 0u);
+            int nB = __popc(bB), nL = __popc(bL), P = E;
+            int slot = (bB & lanebit) ? __popc(bB & lt) : (bL & lanebit) ? nB + __popc(bL & lt) : nB + nL + (int)lane - __popc((bB | bL) & lt);
+            if (chunk) {   // a chunk of a bucket is a batch of its own: P pairs of one class
+                E = 1;
+                P = (int)(ef0 >> 29) + 1;
+                nB = (ml0 != 0u && mh0 != 0u) ? P : 0;
+                nL = (mh0 == 0u) ? P : 0;
+            }
+            // (the max-reduces leave the trip counts in uniform registers: the loops below are provably convergent)
+            P = __reduce_max_sync(0xffffffffu, P);
+            nB = __reduce_max_sync(0xffffffffu, nB);
+            nL = __reduce_max_sync(0xffffffffu, nL);
+            const int top = sp - 1;
+            sp -= E;
+            // ---- load: 8 pair records (4 x 16 B each) per warp-wide load; entry e goes to its class slot
+#pragma unroll
+            for (int it = 0; it < TRAV_BATCH / 8; ++it) {
+                const int e = it * 8 + (int)(lane >> 2);
+                int sl = __shfl_sync(0xffffffffu, slot, e);
+                if (e < P) {
+                    unsigned first, mlo, mhi;
+                    if (chunk) { first = (ef0 & TRAV_FIRST_MASK) + (unsigned)e; mlo = ml0; mhi = mh0; sl = e; }
+                    else { first = ws.stk_first[top - e]; mlo = ws.stk_lo[top - e]; mhi = ws.stk_hi[top - e]; }
+                    float4 v = __ldg(&recs[4 * (int64_t)first + (lane & 3u)]);
+                    if ((lane & 3u) == 2u) { v.z = __uint_as_float(mlo); v.w = __uint_as_float(mhi); }
+                    ws.stage[(lane & 3u) * TRAV_AREA + sl] = v;
+                }
+            }
+            __syncwarp();
+            // ---- eval, one loop per class
+            const int jL = nB + nL;
+#pragma unroll U64_BOTH
+            for (int j = 0; j < nB; ++j) {
+                const float4 XY = sXY[j];
+                const float4 ZM = sZM[j];
+                const float4 TM = sTM[j];
+                uint4 om;
+                eval_pair<COUNT>(XY, ZM, TM.x, TM.y, __float_as_uint(TM.z), lanebit, eps22, A, om.x, om.y);
+                eval_pair<COUNT>(XY, ZM, TM.x, TM.y, __float_as_uint(TM.w), lanebit, eps22, B, om.z, om.w);
+                if (lane == 0) sOP[j] = om;
+            }
+#pragma unroll U64_ONE
+            for (int j = nB; j < jL; ++j) {
+                const float4 XY = sXY[j];
+                const float4 ZM = sZM[j];
+                const float4 TM = sTM[j];
+                uint4 om = make_uint4(0u, 0u, 0u, 0u);
+                eval_pair<COUNT>(XY, ZM, TM.x, TM.y, __float_as_uint(TM.z), lanebit, eps22, A, om.x, om.y);
+                if (lane == 0) sOP[j] = om;
+            }
+#pragma unroll U64_ONE
+            for (int j = jL; j < P; ++j) {
+                const float4 XY = sXY[j];
+                const float4 ZM = sZM[j];
+                const float4 TM = sTM[j];
+                uint4 om = make_uint4(0u, 0u, 0u, 0u);
+                eval_pair<COUNT>(XY, ZM, TM.x, TM.y, __float_as_uint(TM.w), lanebit, eps22, B, om.z, om.w);
+                if (lane == 0) sOP[j] = om;
+            }
+            slots_a += jL;
+            slots_b += nB + (P - jL);
+            __syncwarp();
+            // ---- expand: lane j owns pair slot j
+            unsigned f0 = 0, f1 = 0, n0 = 0, n1 = 0;
+            uint4 om = make_uint4(0u, 0u, 0u, 0u);
+            if ((int)lane < P) {
+                om = sOP[lane];
+                const float4 tm = sTM[lane];   // the ballots include the lanes outside the masks
+                om.x &= __float_as_uint(tm.z); om.y &= __float_as_uint(tm.z);
+                om.z &= __float_as_uint(tm.w); om.w &= __float_as_uint(tm.w);
+                const float4 fn = sFN[lane];
+                f0 = __float_as_uint(fn.x); f1 = __float_as_uint(fn.y);
+                n0 = __float_as_uint(fn.z); n1 = __float_as_uint(fn.w);
+            }
+            const bool c0 = (om.x | om.z) != 0u && n0 != 0u, c1 = (om.y | om.w) != 0u && n1 != 0u;
+            const int np0 = c0 ? (int)((n0 + 1u) >> 1) : 0, np1 = c1 ? (int)((n1 + 1u) >> 1) : 0;
+            const bool big = np0 > TRAV_CELL_PAIRS || np1 > TRAV_CELL_PAIRS;
+            if (!__any_sync(0xffffffffu, big)) {
+                const unsigned k = (unsigned)(np0 + np1);
+                const unsigned b0 = __ballot_sync(0xffffffffu, (k & 1u) != 0u), b1 = __ballot_sync(0xffffffffu, (k & 2u) != 0u);
+                const unsigned b2 = __ballot_sync(0xffffffffu, (k & 4u) != 0u), b3 = __ballot_sync(0xffffffffu, (k & 8u) != 0u);
+                const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
+                if (sp + total > TRAV_CAP) {   // cannot happen (see the stack bound above); never drop silently
+                    if (lane == 0) atomicOr(error, (unsigned)ERR_STACK_OVERFLOW);
+                    sp = 0;
+                } else {
+                    int pos = sp + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) + 8 * __popc(b3 & lt);
+                    for (int q = 0; q < np0; ++q, ++pos) { ws.stk_first[pos] = f0 + (unsigned)q; ws.stk_lo[pos] = om.x; ws.stk_hi[pos] = om.z; }
+                    for (int q = 0; q < np1; ++q, ++pos) { ws.stk_first[pos] = f1 + (unsigned)q; ws.stk_lo[pos] = om.y; ws.stk_hi[pos] = om.w; }
+                    sp += total;
+                }
+            } else {
+                // rare: a bucket of > 8 bodies sharing one finest-level cell is pushed in chunks of <= 8 pairs
+                const int e0 = (np0 + TRAV_CHUNK_PAIRS - 1) / TRAV_CHUNK_PAIRS;
+                const int e1 = (np1 + TRAV_CHUNK_PAIRS - 1) / TRAV_CHUNK_PAIRS;
+                int inc2 = e0 + e1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, inc2, o);
+                    if ((int)lane >= o) inc2 += u;
+                }
+                const int total = __reduce_add_sync(0xffffffffu, e0 + e1);
+                if (sp + total > TRAV_CAP) {   // never drop silently
+                    if (lane == 0) atomicOr(error, (unsigned)ERR_STACK_OVERFLOW);
+                    sp = 0;
+                } else {
+                    int pos = sp + inc2 - (e0 + e1);
+                    for (int q = 0; q < e0; ++q, ++pos) {
+                        const int r = min(np0 - TRAV_CHUNK_PAIRS * q, TRAV_CHUNK_PAIRS);
+                        ws.stk_first[pos] = (f0 + (unsigned)(TRAV_CHUNK_PAIRS * q)) | ((unsigned)(r - 1) << 29);
+                        ws.stk_lo[pos] = om.x; ws.stk_hi[pos] = om.z;
+                    }
+                    for (int q = 0; q < e1; ++q, ++pos) {
+                        const int r = min(np1 - TRAV_CHUNK_PAIRS * q, TRAV_CHUNK_PAIRS);
+                        ws.stk_first[pos] = (f1 + (unsigned)(TRAV_CHUNK_PAIRS * q)) | ((unsigned)(r - 1) << 29);
+                        ws.stk_lo[pos] = om.y; ws.stk_hi[pos] = om.w;
+                    }
+                    sp += total;
+                }
+            }
+            sp = __reduce_max_sync(0xffffffffu, sp);   // uniform register: the walk loop is provably convergent
+            if (COUNT) { ++w_batches; w_both += (unsigned)nB; w_spmax = max(w_spmax, sp); }
+            __syncwarp();
+        }
+        // acc.w: exact interaction count (COUNT) or the half-tile's evaluated pair slots (a cost proxy)
+        if (va) acc[ka] = make_float4(G * (A.ax.x + A.ax.y), G * (A.ay.x + A.ay.y), G * (A.az.x + A.az.y), __int_as_float(COUNT ? A.cnt : slots_a));
+        if (vb) acc[kb] = make_float4(G * (B.ax.x + B.ax.y), G * (B.ay.x + B.ay.y), G * (B.az.x + B.az.y), __int_as_float(COUNT ? B.cnt : slots_b));
+        if (COUNT) {
+            unsigned c32 = (va ? (unsigned)A.cnt : 0u) + (vb ? (unsigned)B.cnt : 0u), l32 = (unsigned)(A.lanepairs + B.lanepairs);
+            for (int o = 16; o > 0; o >>= 1) {
+                c32 += __shfl_xor_sync(0xffffffffu, c32, o);
+                l32 += __shfl_xor_sync(0xffffffffu, l32, o);
+            }
+            w_inter += c32;
+            w_lanepairs += l32;
+            w_slots += (unsigned)(slots_a + slots_b);
+        }
+    }
+    if (COUNT && lane == 0) {
+        if (w_inter) atomicAdd(&counters[0], w_inter);
+        atomicAdd(&counters[1], w_slots);
+        atomicAdd(&counters[2], w_lanepairs);
+        atomicAdd(&counters[3], w_batches);
+        atomicMax(&counters[4], (unsigned long long)w_spmax);
+        atomicAdd(&counters[5], w_both);
+    }
+}
+
+// ---------------------------------------------------------------------------- transposed walk
+// Same per-body MAC semantics and the same batched stack walk as above, with the roles of lanes
+// and loop swapped: a warp owns TB = 8 consecutive sorted bodies; in a batch every LANE holds up to
+// TK pair records in registers (loaded straight from global memory, no staging) and the eval loop
+// runs over the 8 BODIES, whose coordinates are warp-uniform.  Consequences:
+//   * the inner loop has no shared-memory traffic and no warp votes: a lane ORs its own pair's
+//     "open" bit per body into a register; pure FADD2/FFMA2/FMUL2 + MUFU.RSQ work
+//   * a pair is evaluated for the union of only 8 bodies' needs (not 32): fewer wasted lanes
+//   * per-lane partial accelerations of the 8 bodies (24 packed accumulators) are reduced across
+//     the warp once per tile with a halving butterfly (27 shuffles).
+constexpr int TB = 8;                     // bodies per warp tile
+constexpr int TK = 2;                     // pair slots per lane per batch
+constexpr int T2_SLOTS = 32 * TK;
+constexpr int T2_CAP = 512;               // stack entries per warp
+constexpr int T2_MARK = T2_CAP - 2 * T2_SLOTS - 160;   // above this, pop one entry per batch (DFS bound 7 * 21 = 147)
+constexpr int T2_GROUP = 4;               // tiles fetched per atomic (= 32 bodies, the shard granularity)
+
+struct __align__(16) WarpShared2 {
+    unsigned stk_first[T2_CAP];
+    unsigned stk_mask[T2_CAP];
+    unsigned d_first[T2_SLOTS];
+    unsigned d_mask[T2_SLOTS];
+};
+constexpr size_t T2_SMEM_BYTES = sizeof(WarpShared2) * TRAV_WARPS;
+
+__device__ __forceinline__ float bcast_lane(float v, unsigned lane, int src)
+{
+    // the OR-reduce leaves the value in a uniform register (warp-uniform by construction)
+    return __uint_as_float(__reduce_or_sync(0xffffffffu, (int)lane == src ? __float_as_uint(v) : 0u));
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRAV_BLOCK, 2) traverse_t_kernel(const float4* __restrict__ recs, const float4* __restrict__ posm,
+                                                                   float4* __restrict__ acc, int group_begin, int group_end, int n,
+                                                                   float eps2, float G, unsigned* tile_counter,
+                                                                   unsigned long long* counters, unsigned* error)
+{
+    extern __shared__ __align__(16) unsigned char trav_smem[];
+    const unsigned lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    WarpShared2& ws = reinterpret_cast<WarpShared2*>(trav_smem)[threadIdx.x >> 5];
+    const float2 eps22 = make_float2(eps2, eps2);
+    unsigned long long w_inter = 0, w_slots = 0, w_lanepairs = 0, w_batches = 0;
+    int w_spmax = 0;
+
+    for (;;) {
+        unsigned g = 0;
+        if (lane == 0) g = atomicAdd(tile_counter, 1u);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        const int group = group_begin + (int)g;
+        if (group >= group_end) break;
+        for (int sub = 0; sub < T2_GROUP; ++sub) {
+            const int k0 = (group * T2_GROUP + sub) * TB;     // first body of the tile
+            if (k0 >= n) break;
+            const bool valid = (int)lane < TB && k0 + (int)lane < n;
+            const float4 p = valid ? posm[k0 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float nbx[TB], nby[TB], nbz[TB];
+#pragma unroll
+            for (int b = 0; b < TB; ++b) {
+                nbx[b] = -bcast_lane(p.x, lane, b);
+                nby[b] = -bcast_lane(p.y, lane, b);
+                nbz[b] = -bcast_lane(p.z, lane, b);
+            }
+            float2 ax[TB], ay[TB], az[TB];
+#pragma unroll
+            for (int b = 0; b < TB; ++b) ax[b] = ay[b] = az[b] = make_float2(0.f, 0.f);
+            int cnt = 0, lanepairs = 0, slots = 0;
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0) { ws.stk_first[0] = 0u; ws.stk_mask[0] = vmask; }   // pair 0 = {root, dummy}
+            int sp = 1;
+            __syncwarp();
+            while (sp > 0) {
+                // ---- select
+                const int idx = sp - 1 - (int)lane;
+                unsigned ef = 0, em = 0;
+                int np = 0;
+                if (idx >= 0) { ef = ws.stk_first[idx]; em = ws.stk_mask[idx]; np = (int)(ef >> 29) + 1; }
+                int incl = np;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                    if ((int)lane >= o) incl += u;
+                }
+                const int limit = sp > T2_MARK ? 1 : 32;
+                const bool take = idx >= 0 && incl <= T2_SLOTS && (int)lane < limit;
+                const int E = __popc(__ballot_sync(0xffffffffu, take));
+                const int P = __reduce_max_sync(0xffffffffu, (int)lane == E - 1 ? incl : 0);
+                sp -= E;
+                if ((int)lane < E) {
+                    const int base = incl - np;
+                    const unsigned f = ef & TRAV_FIRST_MASK;
+                    for (int q = 0; q < np; ++q) { ws.d_first[base + q] = f + q; ws.d_mask[base + q] = em; }
+                }
+                __syncwarp();
+                // ---- load: lane holds pair slots lane, lane + 32, ...
+                float2 X[TK], Y[TK], Z[TK], M[TK], T[TK];
+                unsigned mk[TK], f0[TK], f1[TK], n0[TK], n1[TK], om0[TK], om1[TK];
+#pragma unroll
+                for (int k = 0; k < TK; ++k) {
+                    const int slot = (int)lane + 32 * k;
+                    X[k] = make_float2(REC_DUMMY_X, REC_DUMMY_X);
+                    Y[k] = Z[k] = M[k] = T[k] = make_float2(0.f, 0.f);
+                    mk[k] = f0[k] = f1[k] = n0[k] = n1[k] = 0u;
+                    om0[k] = om1[k] = 0u;
+                    if (slot < P) {
+                        const float4* r = recs + 4 * (int64_t)ws.d_first[slot];
+                        const float4 q0 = __ldg(r), q1 = __ldg(r + 1), q2 = __ldg(r + 2), q3 = __ldg(r + 3);
+                        mk[k] = ws.d_mask[slot];
+                        X[k] = make_float2(q0.x, q0.y); Y[k] = make_float2(q0.z, q0.w);
+                        Z[k] = make_float2(q1.x, q1.y); M[k] = make_float2(q1.z, q1.w);
+                        T[k] = make_float2(q2.x, q2.y);
+                        f0[k] = __float_as_uint(q3.x); f1[k] = __float_as_uint(q3.y);
+                        n0[k] = __float_as_uint(q3.z); n1[k] = __float_as_uint(q3.w);
+                    }
+                }
+                // ---- eval: every lane evaluates its pairs against the 8 bodies
+#pragma unroll
+                for (int k = 0; k < TK; ++k) {
+                    if (32 * k < P) {   // warp-uniform
+#pragma unroll
+                        for (int b = 0; b < TB; ++b) {
+                            const bool in = (mk[k] >> b) & 1u;
+                            const float nqx = in ? nbx[b] : -REC_LANE_SENTINEL;
+                            const float2 dx = __fadd2_rn(X[k], make_float2(nqx, nqx));
+                            const float2 dy = __fadd2_rn(Y[k], make_float2(nby[b], nby[b]));
+                            const float2 dz = __fadd2_rn(Z[k], make_float2(nbz[b], nbz[b]));
+                            const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, eps22)));
+                            const bool o0 = d2.x <= T[k].x, o1 = d2.y <= T[k].y;
+                            if (o0) om0[k] |= 1u << b;
+                            if (o1) om1[k] |= 1u << b;
+                            float2 r;
+                            r.x = o0 ? 0.f : rsqrt_approx(d2.x);
+                            r.y = o1 ? 0.f : rsqrt_approx(d2.y);
+                            if (COUNT) {
+                                if (in) {
+                                    ++lanepairs;
+                                    if (!o0 && X[k].x < 2e18f) ++cnt;
+                                    if (!o1 && X[k].y < 2e18f) ++cnt;
+                                }
+                            }
+                            const float2 f = __fmul2_rn(M[k], __fmul2_rn(__fmul2_rn(r, r), r));
+                            ax[b] = __ffma2_rn(dx, f, ax[b]);
+                            ay[b] = __ffma2_rn(dy, f, ay[b]);
+                            az[b] = __ffma2_rn(dz, f, az[b]);
+                        }
+                    }
+                }
+                slots += P;
+                // ---- expand: every lane pushes the cells its own pairs must open (slot order)
+                bool big = false;
+                int mine = 0;
+                bool c0[TK], c1[TK];
+                int np0[TK], np1[TK];
+#pragma unroll
+                for (int k = 0; k < TK; ++k) {
+                    c0[k] = om0[k] != 0u && n0[k] != 0u;
+                    c1[k] = om1[k] != 0u && n1[k] != 0u;
+                    np0[k] = (int)((n0[k] + 1u) >> 1);
+                    np1[k] = (int)((n1[k] + 1u) >> 1);
+                    big = big || (c0[k] && np0[k] > TRAV_CHUNK_PAIRS) || (c1[k] && np1[k] > TRAV_CHUNK_PAIRS);
+                }
+                if (!__any_sync(0xffffffffu, big)) {
+#pragma unroll
+                    for (int k = 0; k < TK; ++k) {
+                        if (32 * k < P) {
+                            const unsigned b0 = __ballot_sync(0xffffffffu, c0[k]), b1 = __ballot_sync(0xffffffffu, c1[k]);
+                            int pos = sp + __popc(b0 & lt) + __popc(b1 & lt);
+                            if (c0[k]) { ws.stk_first[pos] = f0[k] | ((unsigned)(np0[k] - 1) << 29); ws.stk_mask[pos] = om0[k]; ++pos; }
+                            if (c1[k]) { ws.stk_first[pos] = f1[k] | ((unsigned)(np1[k] - 1) << 29); ws.stk_mask[pos] = om1[k]; }
+                            sp += __popc(b0) + __popc(b1);
+                        }
+                    }
+                } else {
+                    // rare: a bucket of > 16 bodies sharing one finest-level cell is pushed in chunks
+#pragma unroll
+                    for (int k = 0; k < TK; ++k) {
+                        if (c0[k]) mine += (np0[k] + TRAV_CHUNK_PAIRS - 1) / TRAV_CHUNK_PAIRS;
+                        if (c1[k]) mine += (np1[k] + TRAV_CHUNK_PAIRS - 1) / TRAV_CHUNK_PAIRS;
+                    }
+                    int inc2 = mine;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int u = __shfl_up_sync(0xffffffffu, inc2, o);
+                        if ((int)lane >= o) inc2 += u;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, inc2, 31);
+                    if (sp + total > T2_CAP) {   // never drop silently
+                        if (lane == 0) atomicOr(error, (unsigned)ERR_STACK_OVERFLOW);
+                        sp = 0;
+                    } else {
+                        int pos = sp + inc2 - mine;
+#pragma unroll
+                        for (int k = 0; k < TK; ++k) {
+                            if (c0[k])
+                                for (int q = 0; q * TRAV_CHUNK_PAIRS < np0[k]; ++q, ++pos) {
+                                    const int r = min(np0[k] - TRAV_CHUNK_PAIRS * q, TRAV_CHUNK_PAIRS);
+                                    ws.stk_first[pos] = (f0[k] + (unsigned)(TRAV_CHUNK_PAIRS * q)) | ((unsigned)(r - 1) << 29);
+                                    ws.stk_mask[pos] = om0[k];
+                                }
+                            if (c1[k])
+                                for (int q = 0; q * TRAV_CHUNK_PAIRS < np1[k]; ++q, ++pos) {
+                                    const int r = min(np1[k] - TRAV_CHUNK_PAIRS * q, TRAV_CHUNK_PAIRS);
+                                    ws.stk_first[pos] = (f1[k] + (unsigned)(TRAV_CHUNK_PAIRS * q)) | ((unsigned)(r - 1) << 29);
+                                    ws.stk_mask[pos] = om1[k];
+                                }
+                        }
+                        sp += total;
+                    }
+                }
+                if (COUNT) { ++w_batches; w_spmax = max(w_spmax, sp); }
+                __syncwarp();
+            }
+            // ---- reduce the 24 partial sums over the warp: three halvings over the bodies, then two
+            // plain butterfly steps; lane (b << 2) ends up with body b
+            float v[3 * TB];
+#pragma unroll
+            for (int b = 0; b < TB; ++b) {
+                v[3 * b] = ax[b].x + ax[b].y;
+                v[3 * b + 1] = ay[b].x + ay[b].y;
+                v[3 * b + 2] = az[b].x + az[b].y;
+            }
+#pragma unroll
+            for (int half = 3 * TB / 2, bit = 16; half >= 3; half >>= 1, bit >>= 1) {
+                const bool upper = (lane & (unsigned)bit) != 0u;
+#pragma unroll
+                for (int i = 0; i < half; ++i) {
+                    const float send = upper ? v[i] : v[i + half];
+                    const float keep = upper ? v[i + half] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                v[i] += __shfl_xor_sync(0xffffffffu, v[i], 2);
+                v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
+            }
+            const int body = (int)(lane >> 2);
+            // acc.w: the tile's evaluated pair slots (a cost proxy for load balancing)
+            if ((lane & 3u) == 0u && k0 + body < n)
+                acc[k0 + body] = make_float4(G * v[0], G * v[1], G * v[2], __int_as_float(slots));
+            if (COUNT) {
+                unsigned c32 = (unsigned)cnt, l32 = (unsigned)lanepairs;
+                for (int o = 16; o > 0; o >>= 1) {
+                    c32 += __shfl_xor_sync(0xffffffffu, c32, o);
+                    l32 += __shfl_xor_sync(0xffffffffu, l32, o);
+                }
+                w_inter += c32;
+                w_lanepairs += l32;
+                w_slots += (unsigned)slots;
+            }
+        }
+    }
+    if (COUNT && lane == 0) {
+        if (w_inter) atomicAdd(&counters[0], w_inter);
+        atomicAdd(&counters[1], w_slots);
+        atomicAdd(&counters[2], w_lanepairs);
+        atomicAdd(&counters[3], w_batches);
+        atomicMax(&counters[4], (unsigned long long)w_spmax);
+    }
+}
+
