@@ -649,12 +649,6 @@ __global__ void __launch_bounds__(256) iota_kernel(uint32_t* __restrict__ p, int
     if (i < n) p[i] = (uint32_t)i;
 }
 
-__global__ void __launch_bounds__(256) scatter_mass_kernel(const double* __restrict__ mass_in, const uint32_t* __restrict__ id,
-                                                           double* __restrict__ mass_out, int n)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) mass_out[id[k]] = mass_in[k];
-}
 
 // ============================================================================ host side
 template <typename T>
@@ -682,6 +676,7 @@ void nbody_alloc(NBodySim& s, int n)
         s.keys[b] = alloc_counted<uint64_t>(s, N);
         s.vals[b] = alloc_counted<uint32_t>(s, N);
     }
+    s.mass0 = alloc_counted<double>(s, N);
     s.sorter.init(n);
     s.bytes_allocated += s.sorter.bytes();
     s.posm = alloc_counted<float4>(s, N);
@@ -744,6 +739,7 @@ void nbody_free(NBodySim& s)
         cudaFree(s.pos[b]); cudaFree(s.vel[b]); cudaFree(s.mass[b]); cudaFree(s.id[b]);
         cudaFree(s.keys[b]); cudaFree(s.vals[b]);
     }
+    cudaFree(s.mass0);
     s.sorter.destroy();
     if (s.ms_keys) { cudaFree(s.ms_keys); cudaFree(s.ms_vals); s.ms_keys = nullptr; s.ms_vals = nullptr; }
     cudaFree(s.posm); cudaFree(s.acc); cudaFree(s.childL); cudaFree(s.childR); cudaFree(s.parent);
@@ -782,6 +778,7 @@ void nbody_upload(NBodySim& s, const double* pos, const double* vel, const doubl
     B200_CHECK(cudaMemcpyAsync(s.pos[0], pos, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     B200_CHECK(cudaMemcpyAsync(s.vel[0], vel, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     B200_CHECK(cudaMemcpyAsync(s.mass[0], mass, N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    B200_CHECK(cudaMemcpyAsync(s.mass0, s.mass[0], N * sizeof(double), cudaMemcpyDeviceToDevice, s.stream));   // creation order, kept
     if (s.n > 0) iota_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.id[0], s.n);
     recompute_maxabs(s);
     s.tree_valid = false;
@@ -799,7 +796,8 @@ void nbody_upload_state(NBodySim& s, const double* pos, const double* vel)
     B200_CHECK(cudaMemcpyAsync(s.pos[o], pos, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     B200_CHECK(cudaMemcpyAsync(s.vel[o], vel, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     if (s.n > 0) {
-        scatter_mass_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.mass[s.cur], s.id[s.cur], s.mass[o], s.n);
+        // masses back in creation order: a copy of the kept array (a scatter through id[] costs 2 ms at 50 M)
+        B200_CHECK(cudaMemcpyAsync(s.mass[o], s.mass0, (size_t)s.n * sizeof(double), cudaMemcpyDeviceToDevice, s.stream));
         iota_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.id[o], s.n);
     }
     s.cur = o;
@@ -1520,9 +1518,9 @@ void nbody_set_state_commit(NBodySim& s)
     B200_CHECK(cudaMemcpyAsync(s.pos[o], s.up_pos, bytes, cudaMemcpyDeviceToDevice, s.stream));
     B200_CHECK(cudaMemcpyAsync(s.vel[o], s.up_vel, bytes, cudaMemcpyDeviceToDevice, s.stream));
     B200_CHECK(cudaEventRecord(s.ev_upload_consumed, s.stream));
-    scatter_mass_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.mass[s.cur], s.id[s.cur], s.mass[o], s.n);
+    B200_CHECK(cudaMemcpyAsync(s.mass[o], s.mass0, (size_t)s.n * sizeof(double), cudaMemcpyDeviceToDevice, s.stream));
     iota_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.id[o], s.n);
-    s.launches += 2;
+    s.launches += 1;
     B200_CHECK(cudaGetLastError());
     s.cur = o;
     recompute_maxabs(s);

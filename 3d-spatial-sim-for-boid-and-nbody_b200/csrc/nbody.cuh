@@ -52,6 +52,7 @@ struct NBodySim {
     double* pos[2] = {nullptr, nullptr};
     double* vel[2] = {nullptr, nullptr};
     double* mass[2] = {nullptr, nullptr};
+    double* mass0 = nullptr;                  // masses in creation order (what set_state restores without a scatter)
     uint32_t* id[2] = {nullptr, nullptr};
     int cur = 0;
 
