@@ -26,7 +26,13 @@ constexpr unsigned VAL_MASK = ~FLAG_MASK;
 constexpr int MAX_PASSES = 8;
 constexpr int LOOKBACK = 8;          // status words fetched per look-back round
 
-template <typename K> struct Tile { static constexpr int ITEMS = 12; };
+#ifndef RSORT_ITEMS64
+#define RSORT_ITEMS64 12
+#endif
+#ifndef RSORT_MINB
+#define RSORT_MINB 4
+#endif
+template <typename K> struct Tile { static constexpr int ITEMS = RSORT_ITEMS64; };
 template <> struct Tile<uint32_t> { static constexpr int ITEMS = 16; };
 
 // ---------------------------------------------------------------- histogram of all passes
@@ -98,7 +104,7 @@ __device__ __forceinline__ unsigned match_digit(unsigned d)
 
 // ---------------------------------------------------------------- one pass
 template <typename K, int ITEMS, bool IOTA, bool BALLOTS>
-__global__ void __launch_bounds__(BLOCK, 4) onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out,
+__global__ void __launch_bounds__(BLOCK, RSORT_MINB) onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out,
                                                          const uint32_t* __restrict__ vals_in,
                                                          uint32_t* __restrict__ vals_out, int n, int shift,
                                                          const unsigned* __restrict__ digit_start,
