@@ -196,7 +196,7 @@ def test_every_walk_variant_makes_the_reference_mac_decisions(walk, monkeypatch)
     """The three traversal kernels (one body per lane, two bodies per lane, transposed) are forced in
     turn (the default picks per launch): same interaction lists as the oracle -- accelerations within
     the stated tolerance, interaction counts equal -- on a clustered case, a bucket of coincident
-    bodies (multi-pair stack entries), ragged tile ends and a shard that starts mid-array."""
+    bodies (multi-pair stack entries) and ragged tile ends."""
     from b200sim import presets
     monkeypatch.setenv("B200_TRAV", walk)
     pos, vel, mass = presets.generate("collision", 30_011, 400.0, 0.1, 5)
@@ -259,10 +259,13 @@ def test_many_steps_track_oracle_trajectory():
     assert sim.get_stats()["steps"] == 10
 
 
-def test_shard_slices_compose_to_the_full_traversal():
+@pytest.mark.parametrize("walk", ["32", "64"])
+def test_shard_slices_compose_to_the_full_traversal(walk, monkeypatch):
     """Multi-GPU path on one device: traversing the Morton-sorted bodies slice by slice (what each
-    rank does before the all-gather) fills the accelerations buffer exactly like one full pass."""
+    rank does before the all-gather) fills the accelerations buffer exactly like one full pass, with
+    either walk (slices are whole 64-body tiles, so a rank's tiles are tiles of the full pass)."""
     import torch
+    monkeypatch.setenv("B200_TRAV", walk)
     from b200sim import presets
     from b200sim.nbody.sharded import _DeviceArray, partition_equal, slice_size
     n = 40_000
