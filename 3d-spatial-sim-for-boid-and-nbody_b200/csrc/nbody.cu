@@ -715,6 +715,9 @@ void nbody_alloc(NBodySim& s, int n)
     B200_CHECK(cudaFuncSetAttribute(traverse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV_SMEM_BYTES));
     {
         // B200_TRAV = 32 | 64 | t forces a walk; default: chosen per launch (see nbody_traverse)
+        // (tests shrink these to exercise the bucketed un-permute at small n)
+        if (const char* v = getenv("B200_UNPERM_MIN_N")) s.unperm_min_n = atoi(v);
+        if (const char* v = getenv("B200_UNPERM_SHIFT")) s.unperm_shift = max(1, min(30, atoi(v)));
         const char* ng = getenv("B200_NO_GRAPH");   // plain launches instead of the captured step (debugging, A/B timing)
         s.use_graph = !(ng && ng[0] == '1');
         const char* mode = getenv("B200_TRAV");
@@ -1326,6 +1329,7 @@ static void async_init(NBodySim& s)
     for (cudaEvent_t* e : evs) B200_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     s.frame_pos = alloc_counted<float>(s, 3 * N);
     s.frame_col = alloc_counted<float>(s, 3 * N);
+    s.unperm_counts = alloc_counted<unsigned>(s, 2 * 64);
     s.up_pos = alloc_counted<double>(s, 3 * (N + 64));   // + padding rows: equal all-gather slices up to 64 ranks
     s.up_vel = alloc_counted<double>(s, 3 * (N + 64));
 }
@@ -1335,7 +1339,7 @@ static void async_free(NBodySim& s)
     if (!s.up_stream) return;
     cudaStreamSynchronize(s.up_stream);
     cudaStreamSynchronize(s.down_stream);
-    cudaFree(s.frame_pos); cudaFree(s.frame_col); cudaFree(s.up_pos); cudaFree(s.up_vel);
+    cudaFree(s.frame_pos); cudaFree(s.frame_col); cudaFree(s.up_pos); cudaFree(s.up_vel); cudaFree(s.unperm_counts);
     if (s.frame_dpos) { cudaFree(s.frame_dpos); cudaFree(s.frame_dcol); cudaFree(s.frame_pos2); cudaFree(s.frame_col2); s.frame_dpos = s.frame_dcol = nullptr; }
     cudaEventDestroy(s.ev_frame_ready); cudaEventDestroy(s.ev_frame_done);
     cudaEventDestroy(s.ev_upload_done); cudaEventDestroy(s.ev_upload_consumed);
@@ -1357,6 +1361,108 @@ __global__ void __launch_bounds__(256) frame_kernel(const double* __restrict__ p
     fcol[w] = r; fcol[w + 1] = g; fcol[w + 2] = b;
 }
 
+// ---------------------------------------------------------------------------- bucketed un-permute (large n)
+// frame_kernel's un-permute to creation order is a random 12-byte scatter: every store is a partial
+// sector, read-modify-written in DRAM (6.5 ms at 50 M).  For large n the frame is produced in three
+// coalesced passes instead: the bodies are partitioned by the top bits of their creation index into
+// <= 64 buckets of float4 records {x, y, z, id} {r, g, b, -} (scratch: the pair-record pool, free
+// between steps), then scattered bucket by bucket -- a bucket's output window (<= 24 MB) stays in the
+// 126 MB L2, so the partial stores merge into whole sectors before they reach DRAM.
+constexpr int UNP_ITEMS = 16;                 // bodies per thread (4096 per CTA)
+constexpr int UNP_BUCKETS = 64;
+
+__global__ void __launch_bounds__(256) unperm_hist_kernel(const uint32_t* __restrict__ id, int n, int shift, unsigned* __restrict__ counts)
+{
+    __shared__ unsigned h[UNP_BUCKETS];
+    if (threadIdx.x < UNP_BUCKETS) h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * (256 * UNP_ITEMS) + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < UNP_ITEMS; ++i) {
+        const int64_t k = base + (int64_t)i * 256;
+        if (k < n) atomicAdd(&h[id[k] >> shift], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < UNP_BUCKETS && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) unperm_partition_kernel(const double* __restrict__ pos, const double* __restrict__ vel,
+                                                               const uint32_t* __restrict__ id, int n, int shift, double max_speed,
+                                                               const unsigned* __restrict__ counts, unsigned* __restrict__ cursors,
+                                                               float4* __restrict__ rec_a, float4* __restrict__ rec_b)
+{
+    __shared__ unsigned h[UNP_BUCKETS];
+    __shared__ unsigned gbase[UNP_BUCKETS];
+    if (threadIdx.x < UNP_BUCKETS) h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * (256 * UNP_ITEMS) + threadIdx.x;
+    uint32_t ids[UNP_ITEMS];
+#pragma unroll
+    for (int i = 0; i < UNP_ITEMS; ++i) {
+        const int64_t k = base + (int64_t)i * 256;
+        ids[i] = k < n ? id[k] : 0xffffffffu;
+        if (k < n) atomicAdd(&h[ids[i] >> shift], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < UNP_BUCKETS) {
+        unsigned start = 0;
+        for (int b = 0; b < (int)threadIdx.x; ++b) start += counts[b];   // bucket starts: exclusive scan of the global counts
+        const unsigned mine = h[threadIdx.x];
+        gbase[threadIdx.x] = start + (mine ? atomicAdd(&cursors[threadIdx.x], mine) : 0u);
+        h[threadIdx.x] = 0;   // now the CTA-local cursor
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int i = 0; i < UNP_ITEMS; ++i) {
+        const int64_t k = base + (int64_t)i * 256;
+        if (k >= n) continue;
+        const unsigned b = ids[i] >> shift;
+        const unsigned dst = gbase[b] + atomicAdd(&h[b], 1u);
+        const int64_t o = 3 * k;
+        const double vx = vel[o], vy = vel[o + 1], vz = vel[o + 2];
+        float r, g, bl;
+        speed_color(fmin(1.0, sqrt(vx * vx + vy * vy + vz * vz) / max_speed), r, g, bl);
+        rec_a[dst] = make_float4((float)pos[o], (float)pos[o + 1], (float)pos[o + 2], __uint_as_float(ids[i]));
+        rec_b[dst] = make_float4(r, g, bl, 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(256) unperm_scatter_kernel(const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, int n,
+                                                             float* __restrict__ fpos, float* __restrict__ fcol)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = rec_a[i], b = rec_b[i];
+    const int64_t w = 3 * (int64_t)__float_as_uint(a.w);
+    fpos[w] = a.x; fpos[w + 1] = a.y; fpos[w + 2] = a.z;
+    fcol[w] = b.x; fcol[w + 1] = b.y; fcol[w + 2] = b.z;
+}
+
+// colours + creation-order float32 positions of the current state into (fpos, fcol), on the handle's stream
+static void launch_frame(NBodySim& s, float* fpos, float* fcol, double max_speed)
+{
+    const int n = s.n;
+    cudaStream_t st = s.stream;
+    if (n < s.unperm_min_n || !s.unperm_counts) {
+        frame_kernel<<<div_up(n, 256), 256, 0, st>>>(s.pos[s.cur], s.vel[s.cur], s.id[s.cur], fpos, fcol, n, max_speed);
+        ++s.launches;
+    } else {
+        int shift = s.unperm_shift;   // 2^20 creation indices per bucket (24 MB of output), more when n > 64 M
+        while (((int64_t)(n - 1) >> shift) >= UNP_BUCKETS) ++shift;
+        float4* rec_a = s.recs;                    // the pair-record pool (6 n float4) is free between steps
+        float4* rec_b = s.recs + (size_t)n;
+        s.tree_valid = false;
+        B200_CHECK(cudaMemsetAsync(s.unperm_counts, 0, 2 * UNP_BUCKETS * sizeof(unsigned), st));
+        const int blocks = div_up(n, 256 * UNP_ITEMS);
+        unperm_hist_kernel<<<blocks, 256, 0, st>>>(s.id[s.cur], n, shift, s.unperm_counts);
+        unperm_partition_kernel<<<blocks, 256, 0, st>>>(s.pos[s.cur], s.vel[s.cur], s.id[s.cur], n, shift, max_speed, s.unperm_counts,
+                                                        s.unperm_counts + UNP_BUCKETS, rec_a, rec_b);
+        unperm_scatter_kernel<<<div_up(n, 256), 256, 0, st>>>(rec_a, rec_b, n, fpos, fcol);
+        s.launches += 3;
+    }
+    B200_CHECK(cudaGetLastError());
+}
+
 void nbody_frame_begin(NBodySim& s, double max_speed, float* host_pos, float* host_col)
 {
     nbody_frame_begin_rows(s, max_speed, host_pos, host_col, 0, s.n);
@@ -1369,10 +1475,7 @@ void nbody_frame_begin_rows(NBodySim& s, double max_speed, float* host_pos, floa
     if (s.n == 0) return;
     async_init(s);
     if (s.frame_pending) B200_CHECK(cudaStreamWaitEvent(s.stream, s.ev_frame_done, 0));   // staging still being read
-    frame_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.pos[s.cur], s.vel[s.cur], s.id[s.cur], s.frame_pos, s.frame_col, s.n,
-                                                         max_speed);
-    ++s.launches;
-    B200_CHECK(cudaGetLastError());
+    launch_frame(s, s.frame_pos, s.frame_col, max_speed);
     B200_CHECK(cudaEventRecord(s.ev_frame_ready, s.stream));
     B200_CHECK(cudaStreamWaitEvent(s.down_stream, s.ev_frame_ready, 0));
     B200_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= s.n, "frame rows out of range");
@@ -1435,13 +1538,13 @@ void nbody_frame_delta_begin(NBodySim& s, double max_speed, short* host_dpos, sh
     if (s.frame_pending) B200_CHECK(cudaStreamWaitEvent(s.stream, s.ev_frame_done, 0));   // staging still being read
     float* prev_pos = s.frame_pos; float* prev_col = s.frame_col;
     float* cur_pos = s.frame_pos2; float* cur_col = s.frame_col2;
-    frame_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.pos[s.cur], s.vel[s.cur], s.id[s.cur], cur_pos, cur_col, s.n, max_speed);
+    launch_frame(s, cur_pos, cur_col, max_speed);
     const int64_t count = 3 * (int64_t)N, pairs = count / 2;
     frame_delta_kernel<<<(unsigned)((pairs + 1 + 255) / 256), 256, 0, s.stream>>>(
         reinterpret_cast<const float2*>(cur_pos), reinterpret_cast<const float2*>(prev_pos),
         reinterpret_cast<const float2*>(cur_col), reinterpret_cast<const float2*>(prev_col),
         reinterpret_cast<short2*>(s.frame_dpos), reinterpret_cast<short2*>(s.frame_dcol), pairs, count);
-    s.launches += 2;
+    s.launches += 1;
     B200_CHECK(cudaGetLastError());
     // the new frame becomes the "previous frame" (and the staging frame_begin writes to)
     s.frame_pos = cur_pos; s.frame_col = cur_col;

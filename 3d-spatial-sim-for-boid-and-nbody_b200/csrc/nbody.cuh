@@ -110,6 +110,9 @@ struct NBodySim {
     float *frame_pos = nullptr, *frame_col = nullptr;                  // (N,3) f32 staging, creation order
     short *frame_dpos = nullptr, *frame_dcol = nullptr;                // (N,3) int16 delta staging (frame codec), lazily allocated
     float *frame_pos2 = nullptr, *frame_col2 = nullptr;                // second f32 staging: delta frames alternate between the two
+    int unperm_min_n = 4 * 1024 * 1024;                                // below this n the single scatter kernel is used
+    int unperm_shift = 20;
+    unsigned* unperm_counts = nullptr;                                 // bucket counts + cursors of the bucketed un-permute
     bool frame_has_prev = false;                                       // frame_pos / frame_col hold the previous frame
     double *up_pos = nullptr, *up_vel = nullptr;                       // (N,3) f64 staging of a prefetched state
     bool frame_pending = false, upload_pending = false;

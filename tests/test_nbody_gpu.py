@@ -394,6 +394,31 @@ def test_captured_step_is_bit_identical_to_plain_launches(monkeypatch):
     assert s0 == s1 == 21 and l0 == l1
 
 
+def test_bucketed_unpermute_matches_the_single_scatter(monkeypatch):
+    """Large-n frames are un-permuted bucket by bucket (partition by creation index, then scatter inside an
+    L2-sized window); forced at small n with many buckets it must give the bits of the plain getters."""
+    from b200sim import presets
+    monkeypatch.setenv("B200_UNPERM_MIN_N", "1")
+    monkeypatch.setenv("B200_UNPERM_SHIFT", "11")
+    n = 70_001
+    pos, vel, mass = presets.generate("collision", n, 300.0, 0.1, 8)
+    sim = _sim(pos, vel, mass, 0.1, 1.5, theta=0.7)
+    p, c = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+    for _ in range(2):
+        sim.step(0.05)
+        sim.frame_begin(15.0, p, c); sim.frame_wait()
+        sim.compute_colors(15.0)
+        assert np.array_equal(p, sim.get_positions()) and np.array_equal(c, sim.get_colors())
+    dp, dc = np.empty((n, 3), np.int16), np.empty((n, 3), np.int16)
+    sim.step(0.05)
+    sim.frame_delta_begin(15.0, dp, dc); sim.frame_wait()
+    from b200sim import codec
+    assert np.array_equal(dp, codec.delta_payload(sim.get_positions(), p))
+    # the record pool was used as scratch: the next force evaluation rebuilds the tree
+    acc = sim.compute_accelerations()
+    assert np.isfinite(acc).all()
+
+
 def test_device_delta_frames_are_the_recorders_format2_payload(tmp_path):
     """Frame codec: int16 deltas produced on the device equal the recorder's host
     arithmetic int16((frame - prev) * 1000) on the float32 frames (tools/record.py:256-262), bit for
