@@ -27,6 +27,9 @@ static_assert(sizeof(b200_boids_params) == sizeof(b200::BoidsParams), "boids par
     } catch (const b200::CudaError& e) {                 \
         b200::set_error(e.msg);                          \
         return B200_ERR_CUDA;                            \
+    } catch (const b200::StateError& e) {                \
+        b200::set_error(e.msg);                          \
+        return B200_ERR_STATE;                           \
     } catch (const std::exception& e) {                  \
         b200::set_error(e.what());                       \
         return B200_ERR_STATE;                           \
@@ -156,6 +159,7 @@ B200_API int b200_nbody_sync(b200_nbody* h)
     B200_TRY({
         B200_CHECK(cudaSetDevice(h->sim.device));
         B200_CHECK(cudaStreamSynchronize(h->sim.stream));
+        b200::nbody_check_errors(h->sim);   // never return truncated forces silently
     })
 }
 

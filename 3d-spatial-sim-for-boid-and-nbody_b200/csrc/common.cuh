@@ -10,6 +10,8 @@ namespace b200 {
 void set_error(const std::string& msg);   // defined in capi.cu; read back through b200_last_error()
 
 struct CudaError { std::string msg; };
+// a device-side error flag (traversal stack / record pool overflow) or a misuse of the handle: B200_ERR_STATE
+struct StateError { std::string msg; };
 
 #define B200_CHECK(expr)                                                                      \
     do {                                                                                      \

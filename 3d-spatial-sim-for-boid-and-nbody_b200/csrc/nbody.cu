@@ -550,7 +550,7 @@ __global__ void single_body_record_kernel(const float4* __restrict__ posm, float
     store_pair(recs, 0, ChildRec{b.x, b.y, b.z, b.w, eps2, 0, 0, 0}, dummy_child());
 }
 
-#include "traverse.cuh"   // the three traversal kernels (theta-MAC walk)
+#include "traverse.cuh"   // the traversal kernels (theta-MAC walk)
 
 // ============================================================================ integrate
 // v = (v + a dt) * damping; x += v dt (nbody/simulation.py:281-305; CUDA twin
@@ -680,7 +680,7 @@ void nbody_alloc(NBodySim& s, int n)
     s.sorter.init(n);
     s.bytes_allocated += s.sorter.bytes();
     s.posm = alloc_counted<float4>(s, N);
-    s.acc_capacity = (int64_t)N + 32 * 64;   // room for padded equal slices up to 64 ranks
+    s.acc_capacity = (int64_t)N + 64 * 64;   // room for padded equal slices (whole 64-body tiles) up to 64 ranks
     s.acc = alloc_counted<float4>(s, (size_t)s.acc_capacity);
     s.childL = alloc_counted<int>(s, N);
     s.childR = alloc_counted<int>(s, N);
@@ -710,18 +710,21 @@ void nbody_alloc(NBodySim& s, int n)
     s.d_interactions = alloc_counted<unsigned long long>(s, TRAV_COUNTERS);
     s.d_error = alloc_counted<unsigned>(s, 1);
     B200_CHECK(cudaMemset(s.d_error, 0, sizeof(unsigned)));
+    B200_CHECK(cudaHostAlloc(&s.h_error, sizeof(unsigned), cudaHostAllocDefault));
+    *s.h_error = 0;
     B200_CHECK(cudaMemset(s.d_interactions, 0, TRAV_COUNTERS * sizeof(unsigned long long)));
     B200_CHECK(cudaFuncSetAttribute(traverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV_SMEM_BYTES));
     B200_CHECK(cudaFuncSetAttribute(traverse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV_SMEM_BYTES));
     {
-        // B200_TRAV = 32 | 64 | t forces a walk; default: chosen per launch (see nbody_traverse)
+        // B200_TRAV = 32 | 64 forces a walk; default: chosen per launch (see nbody_traverse)
         // (tests shrink these to exercise the bucketed un-permute at small n)
         if (const char* v = getenv("B200_UNPERM_MIN_N")) s.unperm_min_n = atoi(v);
         if (const char* v = getenv("B200_UNPERM_SHIFT")) s.unperm_shift = max(1, min(30, atoi(v)));
+        if (const char* v = getenv("B200_REC_CAPACITY")) s.rec_capacity_override = atoll(v);   // tests: force a record pool overflow
         const char* ng = getenv("B200_NO_GRAPH");   // plain launches instead of the captured step (debugging, A/B timing)
         s.use_graph = !(ng && ng[0] == '1');
         const char* mode = getenv("B200_TRAV");
-        s.trav_mode = !mode ? 0 : mode[0] == 't' ? 8 : mode[0] == '6' ? 64 : 32;
+        s.trav_mode = !mode ? 0 : mode[0] == '6' ? 64 : 32;
     }
     B200_CHECK(cudaFuncSetAttribute(traverse64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV64_SMEM_BYTES));
     B200_CHECK(cudaFuncSetAttribute(traverse64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV64_SMEM_BYTES));
@@ -752,6 +755,7 @@ void nbody_free(NBodySim& s)
     cudaFree(s.d_children);
     cudaFree(s.d_root); cudaFree(s.d_alloc); cudaFree(s.d_tile_counter); cudaFree(s.d_interactions);
     cudaFree(s.d_error);
+    if (s.h_error) { cudaFreeHost(s.h_error); s.h_error = nullptr; }
     s.timer.destroy();
     async_free(s);
     if (s.own_stream) cudaStreamDestroy(s.own_stream);
@@ -986,7 +990,8 @@ static void build_after_sort(NBodySim& s)
         init_build_counters_kernel<<<1, 1, 0, st>>>(s.d_alloc, s.d_children);   // pair 0 is the root's
         const int nb = div_up(n, PFX_BLOCK);
         const ChildrenArgs ca{s.childL, s.childR, s.parent, s.range, s.lvl, s.meta, s.ishead, s.kids,
-                              s.d_alloc, (unsigned)s.rec_capacity, s.d_error, s.d_children};
+                              s.d_alloc, (unsigned)(s.rec_capacity_override > 0 ? min(s.rec_capacity, s.rec_capacity_override) : s.rec_capacity),
+                              s.d_error, s.d_children};
         prefix_kernel<<<nb, 256, 0, st>>>(s.pos[s.cur], s.mass[s.cur], n, s.ploc, s.bex);
         prefix_blocks_kernel<<<1, 1024, 0, st>>>(s.bex, nb);
         count_children_kernel<<<div_up(n - 1, 256), 256, 0, st>>>(n, ca);
@@ -1024,19 +1029,6 @@ void nbody_traverse(NBodySim& s, int begin, int end)
         // lists (large N, large theta: 0.90 of the pair evaluations are shared at 50 M / theta 0.7, 0.80 at
         // 1 M / theta 0.5); measured on B200: -5 % at 50 M / 0.7, +5 % at 1 M / 0.5, break-even near 4 M / 0.7.
         const int mode = s.trav_mode ? s.trav_mode : (s.theta >= 0.65 && s.n >= 8000000 ? 64 : 32);
-        if (mode == 8) {
-            const int blocks = min(div_up(tiles, TRAV_WARPS), s.sm_count * 2);
-            if (s.count_interactions)
-                traverse_t_kernel<true><<<blocks, TRAV_BLOCK, T2_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, tile_begin, tile_end, min(end, s.n),
-                                                                                  eps2, (float)s.G, s.d_tile_counter, s.d_interactions, s.d_error);
-            else
-                traverse_t_kernel<false><<<blocks, TRAV_BLOCK, T2_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, tile_begin, tile_end, min(end, s.n),
-                                                                                   eps2, (float)s.G, s.d_tile_counter, s.d_interactions, s.d_error);
-            ++s.launches;
-            B200_CHECK(cudaGetLastError());
-            s.timer.mark(st);
-            return;
-        }
         if (mode == 64) {
             const int tiles64 = div_up(min(end, s.n) - begin, 64);
             const int blocks = min(div_up(tiles64, TRAV_WARPS), s.sm_count * 3);
@@ -1232,6 +1224,35 @@ double fp32_peak_tflops(int device)
     return best;
 }
 
+// ---------------------------------------------------------------------------- device error flags
+// The traversal (stack overflow) and the record allocator (pool overflow) raise sticky flags in
+// d_error instead of dropping work silently (the reference silently drops, nbody/simulation.py:176,272).
+// Every reference-facing synchronisation point -- sync(), the getters, frame_wait() -- reads them
+// (one 4-byte copy on a stream it already waits for) and fails with B200_ERR_STATE.
+static void throw_if_flagged(unsigned flags)
+{
+    if (!flags) return;
+    char b[256];
+    snprintf(b, sizeof(b), "device error flags %#x (1 = traversal stack overflow, 2 = octree record pool overflow): "
+                           "forces of the affected step(s) are incomplete", flags);
+    throw StateError{std::string(b)};
+}
+
+void nbody_check_errors(NBodySim& s)
+{
+    unsigned flags = 0;
+    B200_CHECK(cudaMemcpy(&flags, s.d_error, sizeof(flags), cudaMemcpyDeviceToHost));
+    throw_if_flagged(flags);
+}
+
+// end of a getter: the flags travel with the data on the same stream
+static void sync_and_check(NBodySim& s)
+{
+    B200_CHECK(cudaMemcpyAsync(s.h_error, s.d_error, sizeof(unsigned), cudaMemcpyDeviceToHost, s.stream));
+    B200_CHECK(cudaStreamSynchronize(s.stream));
+    throw_if_flagged(*s.h_error);
+}
+
 void nbody_compute_colors(NBodySim& s, double max_speed)
 {
     B200_CHECK(cudaSetDevice(s.device));
@@ -1248,7 +1269,7 @@ void nbody_get_positions(NBodySim& s, float* out)
     unpermute3_kernel<float><<<div_up(s.n, 256), 256, 0, s.stream>>>(s.pos[s.cur], s.id[s.cur], (float*)s.stage, s.n);
     B200_CHECK(cudaGetLastError());
     B200_CHECK(cudaMemcpyAsync(out, s.stage, 3 * (size_t)s.n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    B200_CHECK(cudaStreamSynchronize(s.stream));
+    sync_and_check(s);
 }
 
 void nbody_get_positions_f64(NBodySim& s, double* out)
@@ -1258,7 +1279,7 @@ void nbody_get_positions_f64(NBodySim& s, double* out)
     unpermute3_kernel<double><<<div_up(s.n, 256), 256, 0, s.stream>>>(s.pos[s.cur], s.id[s.cur], (double*)s.stage, s.n);
     B200_CHECK(cudaGetLastError());
     B200_CHECK(cudaMemcpyAsync(out, s.stage, 3 * (size_t)s.n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-    B200_CHECK(cudaStreamSynchronize(s.stream));
+    sync_and_check(s);
 }
 
 void nbody_get_velocities(NBodySim& s, double* out)
@@ -1268,7 +1289,7 @@ void nbody_get_velocities(NBodySim& s, double* out)
     unpermute3_kernel<double><<<div_up(s.n, 256), 256, 0, s.stream>>>(s.vel[s.cur], s.id[s.cur], (double*)s.stage, s.n);
     B200_CHECK(cudaGetLastError());
     B200_CHECK(cudaMemcpyAsync(out, s.stage, 3 * (size_t)s.n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-    B200_CHECK(cudaStreamSynchronize(s.stream));
+    sync_and_check(s);
 }
 
 void nbody_get_colors(NBodySim& s, float* out)
@@ -1276,7 +1297,7 @@ void nbody_get_colors(NBodySim& s, float* out)
     B200_CHECK(cudaSetDevice(s.device));
     if (s.n == 0) return;
     B200_CHECK(cudaMemcpyAsync(out, s.colors, 3 * (size_t)s.n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    B200_CHECK(cudaStreamSynchronize(s.stream));
+    sync_and_check(s);
 }
 
 void nbody_get_accelerations(NBodySim& s, float* out)
@@ -1293,7 +1314,7 @@ void nbody_get_accelerations(NBodySim& s, float* out)
     unpermute_acc_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.acc, s.id[s.cur], (float*)s.stage, s.n);
     B200_CHECK(cudaGetLastError());
     B200_CHECK(cudaMemcpyAsync(out, s.stage, 3 * (size_t)s.n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
-    B200_CHECK(cudaStreamSynchronize(s.stream));
+    sync_and_check(s);
 }
 
 void nbody_get_keys(NBodySim& s, uint64_t* out)
@@ -1302,7 +1323,7 @@ void nbody_get_keys(NBodySim& s, uint64_t* out)
     if (s.n == 0) return;
     if (!s.tree_valid) nbody_build_tree(s);
     B200_CHECK(cudaMemcpyAsync(out, s.keys[s.sorted_slot], (size_t)s.n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
-    B200_CHECK(cudaStreamSynchronize(s.stream));
+    sync_and_check(s);
 }
 
 void nbody_get_perm(NBodySim& s, uint32_t* out)
@@ -1311,7 +1332,7 @@ void nbody_get_perm(NBodySim& s, uint32_t* out)
     if (s.n == 0) return;
     if (!s.tree_valid) nbody_build_tree(s);
     B200_CHECK(cudaMemcpyAsync(out, s.id[s.cur], (size_t)s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
-    B200_CHECK(cudaStreamSynchronize(s.stream));
+    sync_and_check(s);
 }
 
 // ---------------------------------------------------------------------------- asynchronous host traffic
@@ -1472,18 +1493,19 @@ void nbody_frame_begin(NBodySim& s, double max_speed, float* host_pos, float* ho
 void nbody_frame_begin_rows(NBodySim& s, double max_speed, float* host_pos, float* host_col, int row_begin, int row_end)
 {
     B200_CHECK(cudaSetDevice(s.device));
+    B200_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= s.n, "frame rows out of range");
     if (s.n == 0) return;
     async_init(s);
     if (s.frame_pending) B200_CHECK(cudaStreamWaitEvent(s.stream, s.ev_frame_done, 0));   // staging still being read
     launch_frame(s, s.frame_pos, s.frame_col, max_speed);
     B200_CHECK(cudaEventRecord(s.ev_frame_ready, s.stream));
     B200_CHECK(cudaStreamWaitEvent(s.down_stream, s.ev_frame_ready, 0));
-    B200_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= s.n, "frame rows out of range");
     const size_t off = 3 * (size_t)row_begin, bytes = 3 * (size_t)(row_end - row_begin) * sizeof(float);
     if (bytes) {
         B200_CHECK(cudaMemcpyAsync(host_pos + off, s.frame_pos + off, bytes, cudaMemcpyDeviceToHost, s.down_stream));
         B200_CHECK(cudaMemcpyAsync(host_col + off, s.frame_col + off, bytes, cudaMemcpyDeviceToHost, s.down_stream));
     }
+    B200_CHECK(cudaMemcpyAsync(s.h_error, s.d_error, sizeof(unsigned), cudaMemcpyDeviceToHost, s.down_stream));
     B200_CHECK(cudaEventRecord(s.ev_frame_done, s.down_stream));
     s.frame_pending = true;
     s.frame_has_prev = true;
@@ -1553,6 +1575,7 @@ void nbody_frame_delta_begin(NBodySim& s, double max_speed, short* host_dpos, sh
     B200_CHECK(cudaStreamWaitEvent(s.down_stream, s.ev_frame_ready, 0));
     B200_CHECK(cudaMemcpyAsync(host_dpos, s.frame_dpos, 3 * N * sizeof(short), cudaMemcpyDeviceToHost, s.down_stream));
     B200_CHECK(cudaMemcpyAsync(host_dcol, s.frame_dcol, 3 * N * sizeof(short), cudaMemcpyDeviceToHost, s.down_stream));
+    B200_CHECK(cudaMemcpyAsync(s.h_error, s.d_error, sizeof(unsigned), cudaMemcpyDeviceToHost, s.down_stream));
     B200_CHECK(cudaEventRecord(s.ev_frame_done, s.down_stream));
     s.frame_pending = true;
 }
@@ -1563,6 +1586,7 @@ void nbody_frame_wait(NBodySim& s)
     if (!s.frame_pending) return;
     B200_CHECK(cudaEventSynchronize(s.ev_frame_done));
     s.frame_pending = false;
+    throw_if_flagged(*s.h_error);   // the frame was produced by steps that overflowed: do not hand it out silently
 }
 
 void nbody_set_state_begin(NBodySim& s, const double* pos, const double* vel)

@@ -84,6 +84,8 @@ struct NBodySim {
     unsigned* d_tile_counter = nullptr;
     unsigned long long* d_interactions = nullptr;
     unsigned* d_error = nullptr;
+    unsigned* h_error = nullptr;              // pinned copy of d_error taken with every frame (checked by frame_wait)
+    int64_t rec_capacity_override = 0;        // B200_REC_CAPACITY: shrinks the record pool (tests force an overflow)
 
     float* colors = nullptr;                  // (N,3) f32, creation order
     void* stage = nullptr;                    // (N,3) f64-sized staging for getters
@@ -96,7 +98,7 @@ struct NBodySim {
     int step_graph_sorted_slot[MAX_STEP_GRAPHS] = {0, 0, 0, 0};
     unsigned step_graph_next = 0;
     bool use_graph = true;
-    int trav_mode = 0;                        // 0: per launch (64 for large N and theta, else 32); 32 / 64: forced; 8: experimental transposed walk
+    int trav_mode = 0;                        // 0: per launch (64 for large N and theta, else 32); 32 / 64: forced
     bool count_interactions = false;          // exact per-body interaction counts in the traversal (slower)
 
     // multi-GPU: this rank traverses sorted bodies [shard_begin, shard_end) (multiples of 32)
@@ -152,6 +154,8 @@ void nbody_step_begin_sorted(NBodySim& s);   // after nbody_ms_sort_local + the 
 void nbody_step_end(NBodySim& s, double dt);
 double fp32_peak_tflops(int device);
 void nbody_compute_colors(NBodySim& s, double max_speed);
+// after a synchronisation: throws StateError if a kernel raised a device error flag (sticky)
+void nbody_check_errors(NBodySim& s);
 void nbody_get_positions(NBodySim& s, float* out);
 void nbody_get_positions_f64(NBodySim& s, double* out);
 void nbody_get_velocities(NBodySim& s, double* out);

@@ -233,7 +233,6 @@ __global__ void __launch_bounds__(BLOCK, RSORT_MINB) onesweep_kernel(const K* __
 #pragma unroll
             for (int k = 0; k < LOOKBACK; ++k)
                 sw[k] = t - k >= 0 ? ld_relaxed_u32(status + (size_t)(t - k) * RADIX + d) : FLAG_INC;
-#pragma unroll
             bool go = true;   // false after the inclusive prefix or the first word that is not published yet
 #pragma unroll
             for (int k = 0; k < LOOKBACK; ++k) {

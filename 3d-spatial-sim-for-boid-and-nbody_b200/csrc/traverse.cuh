@@ -494,265 +494,3 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 3) traverse64_kernel(const float4*
         atomicAdd(&counters[5], w_both);
     }
 }
-
-// ---------------------------------------------------------------------------- transposed walk
-// Same per-body MAC semantics and the same batched stack walk as above, with the roles of lanes
-// and loop swapped: a warp owns TB = 8 consecutive sorted bodies; in a batch every LANE holds up to
-// TK pair records in registers (loaded straight from global memory, no staging) and the eval loop
-// runs over the 8 BODIES, whose coordinates are warp-uniform.  Consequences:
-//   * the inner loop has no shared-memory traffic and no warp votes: a lane ORs its own pair's
-//     "open" bit per body into a register; pure FADD2/FFMA2/FMUL2 + MUFU.RSQ work
-//   * a pair is evaluated for the union of only 8 bodies' needs (not 32): fewer wasted lanes
-//   * per-lane partial accelerations of the 8 bodies (24 packed accumulators) are reduced across
-//     the warp once per tile with a halving butterfly (27 shuffles).
-constexpr int TB = 8;                     // bodies per warp tile
-constexpr int TK = 2;                     // pair slots per lane per batch
-constexpr int T2_SLOTS = 32 * TK;
-constexpr int T2_CAP = 512;               // stack entries per warp
-constexpr int T2_MARK = T2_CAP - 2 * T2_SLOTS - 160;   // above this, pop one entry per batch (DFS bound 7 * 21 = 147)
-constexpr int T2_GROUP = 4;               // tiles fetched per atomic (= 32 bodies, the shard granularity)
-
-struct __align__(16) WarpShared2 {
-    unsigned stk_first[T2_CAP];
-    unsigned stk_mask[T2_CAP];
-    unsigned d_first[T2_SLOTS];
-    unsigned d_mask[T2_SLOTS];
-};
-constexpr size_t T2_SMEM_BYTES = sizeof(WarpShared2) * TRAV_WARPS;
-
-__device__ __forceinline__ float bcast_lane(float v, unsigned lane, int src)
-{
-    // the OR-reduce leaves the value in a uniform register (warp-uniform by construction)
-    return __uint_as_float(__reduce_or_sync(0xffffffffu, (int)lane == src ? __float_as_uint(v) : 0u));
-}
-
-template <bool COUNT>
-__global__ void __launch_bounds__(TRAV_BLOCK, 2) traverse_t_kernel(const float4* __restrict__ recs, const float4* __restrict__ posm,
-                                                                   float4* __restrict__ acc, int group_begin, int group_end, int n,
-                                                                   float eps2, float G, unsigned* tile_counter,
-                                                                   unsigned long long* counters, unsigned* error)
-{
-    extern __shared__ __align__(16) unsigned char trav_smem[];
-    const unsigned lane = lane_id();
-    const unsigned lt = lanemask_lt();
-    WarpShared2& ws = reinterpret_cast<WarpShared2*>(trav_smem)[threadIdx.x >> 5];
-    const float2 eps22 = make_float2(eps2, eps2);
-    unsigned long long w_inter = 0, w_slots = 0, w_lanepairs = 0, w_batches = 0;
-    int w_spmax = 0;
-
-    for (;;) {
-        unsigned g = 0;
-        if (lane == 0) g = atomicAdd(tile_counter, 1u);
-        g = __shfl_sync(0xffffffffu, g, 0);
-        const int group = group_begin + (int)g;
-        if (group >= group_end) break;
-        for (int sub = 0; sub < T2_GROUP; ++sub) {
-            const int k0 = (group * T2_GROUP + sub) * TB;     // first body of the tile
-            if (k0 >= n) break;
-            const bool valid = (int)lane < TB && k0 + (int)lane < n;
-            const float4 p = valid ? posm[k0 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-            float nbx[TB], nby[TB], nbz[TB];
-#pragma unroll
-            for (int b = 0; b < TB; ++b) {
-                nbx[b] = -bcast_lane(p.x, lane, b);
-                nby[b] = -bcast_lane(p.y, lane, b);
-                nbz[b] = -bcast_lane(p.z, lane, b);
-            }
-            float2 ax[TB], ay[TB], az[TB];
-#pragma unroll
-            for (int b = 0; b < TB; ++b) ax[b] = ay[b] = az[b] = make_float2(0.f, 0.f);
-            int cnt = 0, lanepairs = 0, slots = 0;
-            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-            if (lane == 0) { ws.stk_first[0] = 0u; ws.stk_mask[0] = vmask; }   // pair 0 = {root, dummy}
-            int sp = 1;
-            __syncwarp();
-            while (sp > 0) {
-                // ---- select
-                const int idx = sp - 1 - (int)lane;
-                unsigned ef = 0, em = 0;
-                int np = 0;
-                if (idx >= 0) { ef = ws.stk_first[idx]; em = ws.stk_mask[idx]; np = (int)(ef >> 29) + 1; }
-                int incl = np;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int u = __shfl_up_sync(0xffffffffu, incl, o);
-                    if ((int)lane >= o) incl += u;
-                }
-                const int limit = sp > T2_MARK ? 1 : 32;
-                const bool take = idx >= 0 && incl <= T2_SLOTS && (int)lane < limit;
-                const int E = __popc(__ballot_sync(0xffffffffu, take));
-                const int P = __reduce_max_sync(0xffffffffu, (int)lane == E - 1 ? incl : 0);
-                sp -= E;
-                if ((int)lane < E) {
-                    const int base = incl - np;
-                    const unsigned f = ef & TRAV_FIRST_MASK;
-                    for (int q = 0; q < np; ++q) { ws.d_first[base + q] = f + q; ws.d_mask[base + q] = em; }
-                }
-                __syncwarp();
-                // ---- load: lane holds pair slots lane, lane + 32, ...
-                float2 X[TK], Y[TK], Z[TK], M[TK], T[TK];
-                unsigned mk[TK], f0[TK], f1[TK], n0[TK], n1[TK], om0[TK], om1[TK];
-#pragma unroll
-                for (int k = 0; k < TK; ++k) {
-                    const int slot = (int)lane + 32 * k;
-                    X[k] = make_float2(REC_DUMMY_X, REC_DUMMY_X);
-                    Y[k] = Z[k] = M[k] = T[k] = make_float2(0.f, 0.f);
-                    mk[k] = f0[k] = f1[k] = n0[k] = n1[k] = 0u;
-                    om0[k] = om1[k] = 0u;
-                    if (slot < P) {
-                        const float4* r = recs + 4 * (int64_t)ws.d_first[slot];
-                        const float4 q0 = __ldg(r), q1 = __ldg(r + 1), q2 = __ldg(r + 2), q3 = __ldg(r + 3);
-                        mk[k] = ws.d_mask[slot];
-                        X[k] = make_float2(q0.x, q0.y); Y[k] = make_float2(q0.z, q0.w);
-                        Z[k] = make_float2(q1.x, q1.y); M[k] = make_float2(q1.z, q1.w);
-                        T[k] = make_float2(q2.x, q2.y);
-                        f0[k] = __float_as_uint(q3.x); f1[k] = __float_as_uint(q3.y);
-                        n0[k] = __float_as_uint(q3.z); n1[k] = __float_as_uint(q3.w);
-                    }
-                }
-                // ---- eval: every lane evaluates its pairs against the 8 bodies
-#pragma unroll
-                for (int k = 0; k < TK; ++k) {
-                    if (32 * k < P) {   // warp-uniform
-#pragma unroll
-                        for (int b = 0; b < TB; ++b) {
-                            const bool in = (mk[k] >> b) & 1u;
-                            const float nqx = in ? nbx[b] : -REC_LANE_SENTINEL;
-                            const float2 dx = __fadd2_rn(X[k], make_float2(nqx, nqx));
-                            const float2 dy = __fadd2_rn(Y[k], make_float2(nby[b], nby[b]));
-                            const float2 dz = __fadd2_rn(Z[k], make_float2(nbz[b], nbz[b]));
-                            const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, eps22)));
-                            const bool o0 = d2.x <= T[k].x, o1 = d2.y <= T[k].y;
-                            if (o0) om0[k] |= 1u << b;
-                            if (o1) om1[k] |= 1u << b;
-                            float2 r;
-                            r.x = o0 ? 0.f : rsqrt_approx(d2.x);
-                            r.y = o1 ? 0.f : rsqrt_approx(d2.y);
-                            if (COUNT) {
-                                if (in) {
-                                    ++lanepairs;
-                                    if (!o0 && X[k].x < 2e18f) ++cnt;
-                                    if (!o1 && X[k].y < 2e18f) ++cnt;
-                                }
-                            }
-                            const float2 f = __fmul2_rn(M[k], __fmul2_rn(__fmul2_rn(r, r), r));
-                            ax[b] = __ffma2_rn(dx, f, ax[b]);
-                            ay[b] = __ffma2_rn(dy, f, ay[b]);
-                            az[b] = __ffma2_rn(dz, f, az[b]);
-                        }
-                    }
-                }
-                slots += P;
-                // ---- expand: every lane pushes the cells its own pairs must open (slot order)
-                bool big = false;
-                int mine = 0;
-                bool c0[TK], c1[TK];
-                int np0[TK], np1[TK];
-#pragma unroll
-                for (int k = 0; k < TK; ++k) {
-                    c0[k] = om0[k] != 0u && n0[k] != 0u;
-                    c1[k] = om1[k] != 0u && n1[k] != 0u;
-                    np0[k] = (int)((n0[k] + 1u) >> 1);
-                    np1[k] = (int)((n1[k] + 1u) >> 1);
-                    big = big || (c0[k] && np0[k] > TRAV_CHUNK_PAIRS) || (c1[k] && np1[k] > TRAV_CHUNK_PAIRS);
-                }
-                if (!__any_sync(0xffffffffu, big)) {
-#pragma unroll
-                    for (int k = 0; k < TK; ++k) {
-                        if (32 * k < P) {
-                            const unsigned b0 = __ballot_sync(0xffffffffu, c0[k]), b1 = __ballot_sync(0xffffffffu, c1[k]);
-                            int pos = sp + __popc(b0 & lt) + __popc(b1 & lt);
-                            if (c0[k]) { ws.stk_first[pos] = f0[k] | ((unsigned)(np0[k] - 1) << 29); ws.stk_mask[pos] = om0[k]; ++pos; }
-                            if (c1[k]) { ws.stk_first[pos] = f1[k] | ((unsigned)(np1[k] - 1) << 29); ws.stk_mask[pos] = om1[k]; }
-                            sp += __popc(b0) + __popc(b1);
-                        }
-                    }
-                } else {
-                    // rare: a bucket of > 16 bodies sharing one finest-level cell is pushed in chunks
-#pragma unroll
-                    for (int k = 0; k < TK; ++k) {
-                        if (c0[k]) mine += (np0[k] + TRAV_CHUNK_PAIRS - 1) / TRAV_CHUNK_PAIRS;
-                        if (c1[k]) mine += (np1[k] + TRAV_CHUNK_PAIRS - 1) / TRAV_CHUNK_PAIRS;
-                    }
-                    int inc2 = mine;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int u = __shfl_up_sync(0xffffffffu, inc2, o);
-                        if ((int)lane >= o) inc2 += u;
-                    }
-                    const int total = __shfl_sync(0xffffffffu, inc2, 31);
-                    if (sp + total > T2_CAP) {   // never drop silently
-                        if (lane == 0) atomicOr(error, (unsigned)ERR_STACK_OVERFLOW);
-                        sp = 0;
-                    } else {
-                        int pos = sp + inc2 - mine;
-#pragma unroll
-                        for (int k = 0; k < TK; ++k) {
-                            if (c0[k])
-                                for (int q = 0; q * TRAV_CHUNK_PAIRS < np0[k]; ++q, ++pos) {
-                                    const int r = min(np0[k] - TRAV_CHUNK_PAIRS * q, TRAV_CHUNK_PAIRS);
-                                    ws.stk_first[pos] = (f0[k] + (unsigned)(TRAV_CHUNK_PAIRS * q)) | ((unsigned)(r - 1) << 29);
-                                    ws.stk_mask[pos] = om0[k];
-                                }
-                            if (c1[k])
-                                for (int q = 0; q * TRAV_CHUNK_PAIRS < np1[k]; ++q, ++pos) {
-                                    const int r = min(np1[k] - TRAV_CHUNK_PAIRS * q, TRAV_CHUNK_PAIRS);
-                                    ws.stk_first[pos] = (f1[k] + (unsigned)(TRAV_CHUNK_PAIRS * q)) | ((unsigned)(r - 1) << 29);
-                                    ws.stk_mask[pos] = om1[k];
-                                }
-                        }
-                        sp += total;
-                    }
-                }
-                if (COUNT) { ++w_batches; w_spmax = max(w_spmax, sp); }
-                __syncwarp();
-            }
-            // ---- reduce the 24 partial sums over the warp: three halvings over the bodies, then two
-            // plain butterfly steps; lane (b << 2) ends up with body b
-            float v[3 * TB];
-#pragma unroll
-            for (int b = 0; b < TB; ++b) {
-                v[3 * b] = ax[b].x + ax[b].y;
-                v[3 * b + 1] = ay[b].x + ay[b].y;
-                v[3 * b + 2] = az[b].x + az[b].y;
-            }
-#pragma unroll
-            for (int half = 3 * TB / 2, bit = 16; half >= 3; half >>= 1, bit >>= 1) {
-                const bool upper = (lane & (unsigned)bit) != 0u;
-#pragma unroll
-                for (int i = 0; i < half; ++i) {
-                    const float send = upper ? v[i] : v[i + half];
-                    const float keep = upper ? v[i + half] : v[i];
-                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                v[i] += __shfl_xor_sync(0xffffffffu, v[i], 2);
-                v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
-            }
-            const int body = (int)(lane >> 2);
-            // acc.w: the tile's evaluated pair slots (a cost proxy for load balancing)
-            if ((lane & 3u) == 0u && k0 + body < n)
-                acc[k0 + body] = make_float4(G * v[0], G * v[1], G * v[2], __int_as_float(slots));
-            if (COUNT) {
-                unsigned c32 = (unsigned)cnt, l32 = (unsigned)lanepairs;
-                for (int o = 16; o > 0; o >>= 1) {
-                    c32 += __shfl_xor_sync(0xffffffffu, c32, o);
-                    l32 += __shfl_xor_sync(0xffffffffu, l32, o);
-                }
-                w_inter += c32;
-                w_lanepairs += l32;
-                w_slots += (unsigned)slots;
-            }
-        }
-    }
-    if (COUNT && lane == 0) {
-        if (w_inter) atomicAdd(&counters[0], w_inter);
-        atomicAdd(&counters[1], w_slots);
-        atomicAdd(&counters[2], w_lanepairs);
-        atomicAdd(&counters[3], w_batches);
-        atomicMax(&counters[4], (unsigned long long)w_spmax);
-    }
-}
-

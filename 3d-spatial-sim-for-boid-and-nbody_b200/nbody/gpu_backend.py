@@ -31,9 +31,14 @@ class Backend(Enum):  # nbody/gpu_backend.py:29-33 (same members and values)
 
 
 def _check_cuda() -> Tuple[bool, str]:
-    """nbody/gpu_backend.py:58-70, through the C ABI instead of numba.cuda."""
-    if _lib.device_count() > 0:
-        return True, _lib.device_info(0)
+    """nbody/gpu_backend.py:58-70, through the C ABI instead of numba.cuda.  Like the reference's probe
+    it swallows every failure (library not built, no driver): detection then reports the CPU and
+    create_gpu_simulation returns None, so importers that call get_backend() outside a try block keep working."""
+    try:
+        if _lib.device_count() > 0:
+            return True, _lib.device_info(0)
+    except Exception:
+        pass
     return False, ""
 
 
@@ -181,7 +186,7 @@ class B200BarnesHutSimulation:
         (n,3) float32 host buffers (pinned memory for real overlap) finish by ``frame_wait()``."""
         op = self._out(out_positions, (self.n, 3), np.float32)
         oc = self._out(out_colors, (self.n, 3), np.float32)
-        self._frame_refs = (op, oc)   # keep the buffers alive while the copy is in flight
+        self._hold_frame(op, oc)      # keep the buffers alive while the copy is in flight
         fp = C.POINTER(C.c_float)
         if rows is None:
             _lib.check(self._L.b200_nbody_frame_begin(self._handle(), float(max_speed), op.ctypes.data_as(fp), oc.ctypes.data_as(fp)))
@@ -195,13 +200,25 @@ class B200BarnesHutSimulation:
         the device-to-host bytes of ``frame_begin``.  Needs a previous ``frame_begin``/``frame_delta_begin``."""
         dp = self._out(out_pos_delta, (self.n, 3), np.int16)
         dc = self._out(out_col_delta, (self.n, 3), np.int16)
-        self._frame_refs = (dp, dc)
+        self._hold_frame(dp, dc)
         ip = C.POINTER(C.c_int16)
         _lib.check(self._L.b200_nbody_frame_delta_begin(self._handle(), float(max_speed), dp.ctypes.data_as(ip), dc.ctypes.data_as(ip)))
 
+    def _hold_frame(self, *bufs):
+        # a second begin before frame_wait() must not drop the only reference to host buffers the
+        # first copy may still be writing: every in-flight buffer is held until the wait
+        refs = getattr(self, "_frame_refs", None)
+        if refs is None:
+            refs = self._frame_refs = []
+        refs.extend(bufs)
+
     def frame_wait(self):
-        _lib.check(self._L.b200_nbody_frame_wait(self._handle()))
-        self._frame_refs = None
+        """Blocks until the last frame's host buffers are complete; raises if a step that produced it
+        overflowed the traversal stack or the record pool (B200_ERR_STATE)."""
+        try:
+            _lib.check(self._L.b200_nbody_frame_wait(self._handle()))
+        finally:
+            self._frame_refs = None
 
     def set_state_begin(self, positions: np.ndarray, velocities: np.ndarray, rows=None):
         """Start uploading a new state (creation order, fp64) on a side stream; ``set_state_commit()``

@@ -1,0 +1,185 @@
+// evalbench.cu -- the traversal's eval loop in isolation (development aid): how many SMSP clocks one
+// (pair record, 32-lane half) evaluation costs for different loop bodies, without the tree walk.
+//   VAR 0  per-lane MAC (FSETP + VOTE per child, ballots stored by lane 0), two bodies per lane   [shipped "both" loop]
+//   VAR 1  no MAC ("sure accept": the tile-level test has decided), lane mask as MUFU predicate, two bodies per lane
+//   VAR 2  no MAC, no mask (full mask), two bodies per lane
+//   VAR 3  per-lane MAC, one body per lane        VAR 4  no MAC, no mask, one body per lane
+//   VAR 5  per-lane MAC, four bodies per lane     VAR 6  no MAC, no mask, four bodies per lane
+//   VAR 7  pure FFMA2 (clock calibration: 0.5 warp-instr/clk/SMSP)
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o evalbench scripts/evalbench.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
+
+constexpr int AREA = 34;
+
+__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+struct Body { float npx, npy, npz; float2 ax, ay, az; };
+
+template <int MODE>   // 0: MAC  1: masked, no MAC  2: plain
+__device__ __forceinline__ void eval(const float4& XY, const float4& ZM, float T0, float T1, unsigned mask, unsigned lanebit, float2 eps22,
+                                     Body& b, unsigned& om0, unsigned& om1)
+{
+    const float2 dx = __fadd2_rn(make_float2(XY.x, XY.y), make_float2(b.npx, b.npx));
+    const float2 dy = __fadd2_rn(make_float2(XY.z, XY.w), make_float2(b.npy, b.npy));
+    const float2 dz = __fadd2_rn(make_float2(ZM.x, ZM.y), make_float2(b.npz, b.npz));
+    const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, eps22)));
+    float2 r;
+    if (MODE == 0) {
+        const bool in = (mask & lanebit) != 0u;
+        const bool a0 = in && d2.x > T0, a1 = in && d2.y > T1;
+        om0 = __ballot_sync(0xffffffffu, !a0);
+        om1 = __ballot_sync(0xffffffffu, !a1);
+        r.x = a0 ? rsqrt_approx(d2.x) : 0.f;
+        r.y = a1 ? rsqrt_approx(d2.y) : 0.f;
+    } else if (MODE == 1) {
+        const bool in = (mask & lanebit) != 0u;
+        r.x = in ? rsqrt_approx(d2.x) : 0.f;
+        r.y = in ? rsqrt_approx(d2.y) : 0.f;
+    } else {
+        r.x = rsqrt_approx(d2.x);
+        r.y = rsqrt_approx(d2.y);
+    }
+    const float2 f = __fmul2_rn(make_float2(ZM.z, ZM.w), __fmul2_rn(__fmul2_rn(r, r), r));
+    b.ax = __ffma2_rn(dx, f, b.ax);
+    b.ay = __ffma2_rn(dy, f, b.ay);
+    b.az = __ffma2_rn(dz, f, b.az);
+}
+
+template <int MODE, int NB, int MINB>
+__global__ void __launch_bounds__(256, MINB) evalk(float4* out, int iters, int P, float eps2)
+{
+    extern __shared__ __align__(16) float4 sm[];
+    const unsigned lane = threadIdx.x & 31u, lanebit = 1u << lane;
+    float4* st = sm + (threadIdx.x >> 5) * (5 * AREA);
+    float4* sXY = st; float4* sZM = st + AREA; float4* sTM = st + 2 * AREA; uint4* sOP = reinterpret_cast<uint4*>(st + 4 * AREA);
+    for (int j = lane; j < AREA; j += 32) {
+        const float s = 37.f * j + blockIdx.x;
+        sXY[j] = make_float4(s, -s, 0.5f * s, 3.f + s);
+        sZM[j] = make_float4(0.25f * s, 7.f - s, 1.f, 2.f);
+        sTM[j] = make_float4(50.f, (j & 3) ? 50.f : 1e9f, __uint_as_float(0xffffffffu - (j == 5 ? 0xff00u : 0u)), __uint_as_float(0xffffffffu));
+    }
+    __syncwarp();
+    Body b[NB];
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        b[q].npx = -(float)(threadIdx.x + 13 * q); b[q].npy = (float)(blockIdx.x & 63) + q; b[q].npz = 3.f * lane;
+        b[q].ax = b[q].ay = b[q].az = make_float2(0.f, 0.f);
+    }
+    const float2 eps22 = make_float2(eps2, eps2);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 2
+        for (int j = 0; j < P; ++j) {
+            const float4 XY = sXY[j], ZM = sZM[j], TM = sTM[j];
+            unsigned om[2 * NB];
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                om[2 * q] = om[2 * q + 1] = 0u;
+                eval<MODE>(XY, ZM, TM.x, TM.y, __float_as_uint((q & 1) ? TM.w : TM.z), lanebit, eps22, b[q], om[2 * q], om[2 * q + 1]);
+            }
+            if (MODE == 0 && lane == 0) {
+                if (NB == 1) *reinterpret_cast<uint2*>(&sOP[j]) = make_uint2(om[0], om[1]);
+                else sOP[j] = make_uint4(om[0], om[1], om[2], om[3]);
+                if (NB == 4) sOP[j + 0] = make_uint4(om[4], om[5], om[6], om[7]);
+            }
+        }
+        __syncwarp();
+    }
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < NB; ++q) { r.x += b[q].ax.x + b[q].ax.y; r.y += b[q].ay.x + b[q].ay.y; r.z += b[q].az.x + b[q].az.y; }
+    r.w = __uint_as_float(sOP[lane].x);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+__global__ void __launch_bounds__(256) ffma2k(float* out, int iters)
+{
+    float2 x[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) x[c] = make_float2(threadIdx.x + c, threadIdx.x - c);
+    const float2 a = make_float2(1.0000001f, 1.0000001f), bb = make_float2(1e-7f, 1e-7f);
+    for (int i = 0; i < iters; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[c] = __ffma2_rn(x[c], a, bb);
+    float r = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) r += x[c].x + x[c].y;
+    if (r == 12345.678f) out[0] = r;
+}
+
+static double g_mhz = 1965.0;
+static int g_sms = 148;
+
+template <int MODE, int NB, int MINB>
+int run(const char* name, float4* d, int ctas_per_sm)
+{
+    cudaEvent_t e0, e1;
+    CHECK(cudaEventCreate(&e0)); CHECK(cudaEventCreate(&e1));
+    const int iters = 2000, P = 32;
+    // shared memory sized so that exactly ctas_per_sm CTAs fit (like the real kernel's stack + staging)
+    const size_t smem = (size_t)(220 * 1024 / ctas_per_sm) & ~(size_t)1023;
+    CHECK(cudaFuncSetAttribute(evalk<MODE, NB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = g_sms * ctas_per_sm;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CHECK(cudaEventRecord(e0));
+        evalk<MODE, NB, MINB><<<blocks, 256, smem>>>(d, iters, P, 100.f);
+        CHECK(cudaEventRecord(e1));
+        CHECK(cudaEventSynchronize(e1));
+        float ms; CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaFuncAttributes fa; CHECK(cudaFuncGetAttributes(&fa, evalk<MODE, NB, MINB>));
+    const double evals = (double)blocks * 8 * iters * P * NB;
+    const double clk = best * 1e-3 * g_mhz * 1e6 * g_sms * 4 / evals;
+    const double tflops = evals * 64 * 20 / (best * 1e-3) / 1e12;   // 20-flop convention, every lane useful
+    printf("%-46s regs %3d  %d CTA/SM  %8.3f ms  %6.2f clk/eval  %6.2f TFLOP/s(20-flop conv.)\n", name, fa.numRegs, ctas_per_sm, best, clk, tflops);
+    return 0;
+}
+
+int main()
+{
+    cudaDeviceProp p; CHECK(cudaGetDeviceProperties(&p, 0));
+    int khz = 0; CHECK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0));
+    g_mhz = khz / 1000.0; g_sms = p.multiProcessorCount;
+    printf("%s, %d SMs, clock attr %.0f MHz\n", p.name, g_sms, g_mhz);
+    float4* d; CHECK(cudaMalloc(&d, sizeof(float4) * 256 * g_sms * 8));
+    {
+        cudaEvent_t e0, e1; CHECK(cudaEventCreate(&e0)); CHECK(cudaEventCreate(&e1));
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            CHECK(cudaEventRecord(e0));
+            ffma2k<<<g_sms * 8, 256>>>((float*)d, 4096);
+            CHECK(cudaEventRecord(e1)); CHECK(cudaEventSynchronize(e1));
+            float ms; CHECK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        const double wi = 8.0 * 4096 * 8 * g_sms * 8;
+        printf("FFMA2 only: %.3f ms, %.3f warp-instr/clk/SMSP at the nominal clock, %.1f TFLOP/s\n", best,
+               wi / (best * 1e-3 * g_mhz * 1e6 * g_sms * 4), wi * 32 * 4 / (best * 1e-3) / 1e12);
+    }
+    for (int c = 3; c <= 4; ++c) {
+        if (c == 3) {
+            run<0, 2, 3>("MAC, 2 bodies/lane (shipped both-loop)", d, c);
+            run<1, 2, 3>("no MAC, masked, 2 bodies/lane", d, c);
+            run<2, 2, 3>("no MAC, full mask, 2 bodies/lane", d, c);
+            run<0, 1, 3>("MAC, 1 body/lane", d, c);
+            run<2, 1, 3>("no MAC, full mask, 1 body/lane", d, c);
+            run<0, 4, 3>("MAC, 4 bodies/lane", d, c);
+            run<2, 4, 3>("no MAC, full mask, 4 bodies/lane", d, c);
+        } else {
+            run<0, 2, 4>("MAC, 2 bodies/lane (shipped both-loop)", d, c);
+            run<1, 2, 4>("no MAC, masked, 2 bodies/lane", d, c);
+            run<2, 2, 4>("no MAC, full mask, 2 bodies/lane", d, c);
+            run<0, 1, 4>("MAC, 1 body/lane", d, c);
+            run<2, 1, 4>("no MAC, full mask, 1 body/lane", d, c);
+        }
+    }
+    run<0, 2, 2>("MAC, 2 bodies/lane, 2 CTA/SM", d, 2);
+    run<0, 4, 2>("MAC, 4 bodies/lane, 2 CTA/SM", d, 2);
+    run<2, 4, 2>("no MAC, full mask, 4 bodies/lane, 2 CTA/SM", d, 2);
+    cudaFree(d);
+    return 0;
+}
