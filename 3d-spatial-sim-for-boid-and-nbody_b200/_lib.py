@@ -21,6 +21,7 @@ class NBodyStats(C.Structure):
         ("bytes_allocated", C.c_int64), ("timed_steps", C.c_int64), ("phase_ms", C.c_double * N_PHASES),
         ("pair_records", C.c_int64), ("trav_pair_slots", C.c_int64), ("trav_lane_pairs", C.c_int64),
         ("trav_batches", C.c_int64), ("trav_stack_max", C.c_int64), ("trav_shared_pairs", C.c_int64),
+        ("trav_kernel", C.c_int32), ("reserved0", C.c_int32), ("trav_sure_pairs", C.c_int64),
     ]
 
 
@@ -77,6 +78,8 @@ SIGNATURES = {
     "b200_nbody_reset_stats": (C.c_int, [_h]),
     "b200_nbody_set_profiling": (C.c_int, [_h, C.c_int]),
     "b200_nbody_set_counting": (C.c_int, [_h, C.c_int]),
+    "b200_nbody_count_interactions": (C.c_int, [_h, C.POINTER(C.c_int64)]),
+    "b200_nbody_state_checksum": (C.c_int, [_h, C.POINTER(C.c_uint64)]),
     "b200_nbody_timed_steps": (C.c_int, [_h, C.c_double, C.c_int, C.POINTER(C.c_float)]),
     "b200_nbody_launch_count": (C.c_int, [_h, C.POINTER(C.c_int64)]),
     "b200_nbody_frame_begin": (C.c_int, [_h, C.c_double, _fp, _fp]),

@@ -219,6 +219,8 @@ B200_API int b200_nbody_get_stats(b200_nbody* h, b200_nbody_stats* out)
         out->trav_batches = (int64_t)ctr[3];
         out->trav_stack_max = (int64_t)ctr[4];
         out->trav_shared_pairs = (int64_t)ctr[5];
+        out->trav_kernel = s.last_trav_kernel;
+        out->trav_sure_pairs = (int64_t)ctr[6];
         out->error_flags = err;
         out->sm_count = s.sm_count;
         out->bytes_allocated = (int64_t)s.bytes_allocated;
@@ -251,6 +253,18 @@ B200_API int b200_nbody_set_counting(b200_nbody* h, int enabled)
     B200_ARG(h, "handle is null");
     h->sim.count_interactions = enabled != 0;
     return B200_OK;
+}
+
+B200_API int b200_nbody_count_interactions(b200_nbody* h, int64_t* interactions)
+{
+    B200_ARG(h && interactions, "null argument");
+    B200_TRY(*interactions = b200::nbody_count_interactions(h->sim))
+}
+
+B200_API int b200_nbody_state_checksum(b200_nbody* h, uint64_t out[2])
+{
+    B200_ARG(h && out, "null argument");
+    B200_TRY(b200::nbody_state_checksum(h->sim, out))
 }
 
 B200_API int b200_nbody_timed_steps(b200_nbody* h, double dt, int nsteps, float* elapsed_ms)

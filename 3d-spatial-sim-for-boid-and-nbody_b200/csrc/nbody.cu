@@ -724,10 +724,12 @@ void nbody_alloc(NBodySim& s, int n)
         const char* ng = getenv("B200_NO_GRAPH");   // plain launches instead of the captured step (debugging, A/B timing)
         s.use_graph = !(ng && ng[0] == '1');
         const char* mode = getenv("B200_TRAV");
-        s.trav_mode = !mode ? 0 : mode[0] == '6' ? 64 : 32;
+        s.trav_mode = !mode ? 0 : (mode[0] == '6' ? (mode[1] == '4' && mode[2] == 'o' ? 63 : 64) : 32);   // "64o": the unclassed 64-body walk
     }
     B200_CHECK(cudaFuncSetAttribute(traverse64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV64_SMEM_BYTES));
     B200_CHECK(cudaFuncSetAttribute(traverse64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV64_SMEM_BYTES));
+    B200_CHECK(cudaFuncSetAttribute(traverse64c_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV64C_SMEM_BYTES));
+    B200_CHECK(cudaFuncSetAttribute(traverse64c_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV64C_SMEM_BYTES));
     B200_CHECK(cudaMemset(s.colors, 0, 3 * N * sizeof(float)));
     s.shard_begin = 0;
     s.shard_end = n;
@@ -1029,7 +1031,22 @@ void nbody_traverse(NBodySim& s, int begin, int end)
         // lists (large N, large theta: 0.90 of the pair evaluations are shared at 50 M / theta 0.7, 0.80 at
         // 1 M / theta 0.5); measured on B200: -5 % at 50 M / 0.7, +5 % at 1 M / 0.5, break-even near 4 M / 0.7.
         const int mode = s.trav_mode ? s.trav_mode : (s.theta >= 0.65 && s.n >= 8000000 ? 64 : 32);
+        s.last_trav_kernel = mode == 63 ? 64 : mode;
         if (mode == 64) {
+            const int tiles64 = div_up(min(end, s.n) - begin, 64);
+            const int blocks = min(div_up(tiles64, TRAV_WARPS), s.sm_count * 3);
+            if (s.count_interactions)
+                traverse64c_kernel<true><<<blocks, TRAV_BLOCK, TRAV64C_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, begin, min(end, s.n), eps2, (float)s.G,
+                                                                                        s.d_tile_counter, s.d_interactions, s.d_error);
+            else
+                traverse64c_kernel<false><<<blocks, TRAV_BLOCK, TRAV64C_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, begin, min(end, s.n), eps2, (float)s.G,
+                                                                                         s.d_tile_counter, s.d_interactions, s.d_error);
+            ++s.launches;
+            B200_CHECK(cudaGetLastError());
+            s.timer.mark(st);
+            return;
+        }
+        if (mode == 63) {
             const int tiles64 = div_up(min(end, s.n) - begin, 64);
             const int blocks = min(div_up(tiles64, TRAV_WARPS), s.sm_count * 3);
             if (s.count_interactions)
@@ -1315,6 +1332,63 @@ void nbody_get_accelerations(NBodySim& s, float* out)
     B200_CHECK(cudaGetLastError());
     B200_CHECK(cudaMemcpyAsync(out, s.stage, 3 * (size_t)s.n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     sync_and_check(s);
+}
+
+int64_t nbody_count_interactions(NBodySim& s)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    if (s.n == 0) return 0;
+    const bool timing = s.timer.enabled, counting = s.count_interactions;
+    s.timer.enabled = false;
+    s.count_interactions = true;
+    if (!s.tree_valid) nbody_build_tree(s);
+    unsigned long long before = 0, after = 0;
+    B200_CHECK(cudaMemcpyAsync(&before, s.d_interactions, sizeof(before), cudaMemcpyDeviceToHost, s.stream));
+    nbody_traverse(s, s.shard_begin, s.shard_end);
+    s.timer.enabled = timing;
+    s.count_interactions = counting;
+    B200_CHECK(cudaMemcpyAsync(&after, s.d_interactions, sizeof(after), cudaMemcpyDeviceToHost, s.stream));
+    sync_and_check(s);
+    return (int64_t)(after - before);
+}
+
+// sum over bodies of mix(creation index) * (bit patterns of the three components): commutative, so equal for
+// any order of the bodies, and sensitive to a single flipped bit
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x)
+{
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+    return x;
+}
+
+__global__ void __launch_bounds__(256) checksum_kernel(const double* __restrict__ pos, const double* __restrict__ vel,
+                                                       const uint32_t* __restrict__ id, int n, unsigned long long* __restrict__ out)
+{
+    unsigned long long a = 0, b = 0;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long h = mix64(0x9e3779b97f4a7c15ull + id[k]) | 1ull;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            a += mix64(h + d) * (unsigned long long)__double_as_longlong(pos[3 * k + d]);
+            b += mix64(h + 7 + d) * (unsigned long long)__double_as_longlong(vel[3 * k + d]);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if (lane_id() == 0) { atomicAdd(&out[0], a); atomicAdd(&out[1], b); }
+}
+
+void nbody_state_checksum(NBodySim& s, uint64_t out[2])
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    out[0] = out[1] = 0;
+    if (s.n == 0) return;
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(s.stage);   // getter staging: free between calls
+    B200_CHECK(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), s.stream));
+    checksum_kernel<<<min(div_up(s.n, 256), s.sm_count * 8), 256, 0, s.stream>>>(s.pos[s.cur], s.vel[s.cur], s.id[s.cur], s.n, d);
+    B200_CHECK(cudaGetLastError());
+    unsigned long long h[2] = {0, 0};
+    B200_CHECK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s.stream));
+    sync_and_check(s);
+    out[0] = h[0]; out[1] = h[1];
 }
 
 void nbody_get_keys(NBodySim& s, uint64_t* out)

@@ -99,6 +99,7 @@ struct NBodySim {
     unsigned step_graph_next = 0;
     bool use_graph = true;
     int trav_mode = 0;                        // 0: per launch (64 for large N and theta, else 32); 32 / 64: forced
+    int last_trav_kernel = 0;                 // 32 / 64: walk of the last traversal launch
     bool count_interactions = false;          // exact per-body interaction counts in the traversal (slower)
 
     // multi-GPU: this rank traverses sorted bodies [shard_begin, shard_end) (multiples of 32)
@@ -161,6 +162,8 @@ void nbody_get_positions_f64(NBodySim& s, double* out);
 void nbody_get_velocities(NBodySim& s, double* out);
 void nbody_get_colors(NBodySim& s, float* out);
 void nbody_get_accelerations(NBodySim& s, float* out);   // creation order, runs build+traverse if needed
+int64_t nbody_count_interactions(NBodySim& s);           // one counting force pass over the shard, current state
+void nbody_state_checksum(NBodySim& s, uint64_t out[2]);
 void nbody_get_keys(NBodySim& s, uint64_t* out);
 void nbody_get_perm(NBodySim& s, uint32_t* out);
 // frame egress: colours + creation-order fp32 positions on the compute stream, D2H on a second stream

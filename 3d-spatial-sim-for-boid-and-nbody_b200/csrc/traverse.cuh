@@ -494,3 +494,326 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 3) traverse64_kernel(const float4*
         atomicAdd(&counters[5], w_both);
     }
 }
+
+// ---------------------------------------------------------------------------- 64-body walk, classed
+// The per-lane MAC costs more than the arithmetic it guards: on B200 every ALU-pipe instruction (FSETP,
+// VOTE, LOP3) takes about as long as a packed FFMA2 -- the both-halves loop above runs at 36 clk per (pair,
+// half) evaluation, the same loop without the MAC at 27 (scripts/evalbench.cu).  But for most pairs the
+// outcome of the MAC is known for the whole tile before any lane looks: if the axis-aligned box of a
+// 32-body half is farther from a child's centre of mass than that child's MAC radius, EVERY body of the half
+// accepts the child -- each lane would have decided exactly that (the test is conservative by a relative
+// 1e-5, four orders above the fp32 rounding of the lanes' own d^2).  So each lane loads ONE pair record of
+// the batch, classifies it against the two boxes, and the batch is sorted into five classes with a loop each:
+//   FF  both halves need the pair, both surely accept, both masks full  -> arithmetic only
+//   SS  both halves surely accept, partial masks                       -> accumulation predicated by the mask bit
+//   SA / SB  only one half needs the pair, surely accepts
+//   UU  anything else                                                   -> the per-lane MAC loop (as above)
+// Only UU pairs produce "open" ballots and are looked at by the expand step.  The evaluated (pair, half) set
+// and every lane's accept / open decisions are exactly those of the walk above.
+struct __align__(16) WarpShared64C {
+    unsigned stk_first[TRAV_CAP];
+    unsigned stk_lo[TRAV_CAP];
+    unsigned stk_hi[TRAV_CAP];
+    float4 stage[5 * TRAV_AREA];         // class-sorted: XY ZM {T0,T1,mask lo,mask hi} {open lo 0, lo 1, hi 0, hi 1}; selection order: FN
+    float4 box[4];                       // {Alo.xyz, -} {Ahi.xyz, -} {Blo.xyz, -} {Bhi.xyz, -}
+};
+constexpr size_t TRAV64C_SMEM_BYTES = sizeof(WarpShared64C) * TRAV_WARPS;
+constexpr float TRAV_SURE_MARGIN = 1.00001f;
+
+// order-preserving float <-> int map (signed integer compare == float compare), for redux.sync.min/max
+__device__ __forceinline__ int f2ord(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
+// squared distance from the box [lo, hi] to the two children's coordinates along one axis, added to acc
+__device__ __forceinline__ float2 box_axis(float2 c, float lo, float hi, float2 acc)
+{
+    const float q0 = fmaxf(fmaxf(lo - c.x, c.x - hi), 0.f), q1 = fmaxf(fmaxf(lo - c.y, c.y - hi), 0.f);
+    return __ffma2_rn(make_float2(q0, q1), make_float2(q0, q1), acc);
+}
+
+template <bool COUNT, int MODE>   // MODE 1: mask-predicated, no MAC   2: no mask, no MAC
+__device__ __forceinline__ void eval_sure(const float4& XY, const float4& ZM, bool in, float2 eps22, EvalBody& b)
+{
+    const float2 dx = __fadd2_rn(make_float2(XY.x, XY.y), make_float2(b.npx, b.npx));
+    const float2 dy = __fadd2_rn(make_float2(XY.z, XY.w), make_float2(b.npy, b.npy));
+    const float2 dz = __fadd2_rn(make_float2(ZM.x, ZM.y), make_float2(b.npz, b.npz));
+    const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, eps22)));
+    float2 r;
+    r.x = rsqrt_approx(d2.x);
+    r.y = rsqrt_approx(d2.y);
+    const float2 f = __fmul2_rn(make_float2(ZM.z, ZM.w), __fmul2_rn(__fmul2_rn(r, r), r));
+    if (MODE == 2 || in) {
+        b.ax = __ffma2_rn(dx, f, b.ax);
+        b.ay = __ffma2_rn(dy, f, b.ay);
+        b.az = __ffma2_rn(dz, f, b.az);
+    }
+    if (COUNT) {
+        if (in) {
+            ++b.lanepairs;
+            if (XY.x < 2e18f) ++b.cnt;
+            if (XY.y < 2e18f) ++b.cnt;
+        }
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(TRAV_BLOCK, 3) traverse64c_kernel(const float4* __restrict__ recs, const float4* __restrict__ posm,
+                                                                    float4* __restrict__ acc, int begin, int end,
+                                                                    float eps2, float G, unsigned* tile_counter,
+                                                                    unsigned long long* counters, unsigned* error)
+{
+    extern __shared__ __align__(16) unsigned char trav_smem[];
+    const unsigned lane = lane_id();
+    const unsigned lanebit = 1u << lane;
+    const unsigned lt = lanemask_lt();
+    WarpShared64C& ws = reinterpret_cast<WarpShared64C*>(trav_smem)[threadIdx.x >> 5];
+    float4* sXY = ws.stage;
+    float4* sZM = ws.stage + TRAV_AREA;
+    float4* sTM = ws.stage + 2 * TRAV_AREA;
+    uint4* sOP = reinterpret_cast<uint4*>(ws.stage + 3 * TRAV_AREA);
+    float4* sFN = ws.stage + 4 * TRAV_AREA;
+    const float2 eps22 = make_float2(eps2, eps2);
+    unsigned long long w_inter = 0, w_slots = 0, w_lanepairs = 0, w_batches = 0, w_both = 0, w_sure = 0;
+    int w_spmax = 0;
+
+    for (;;) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1u);
+        t = __reduce_max_sync(0xffffffffu, t);
+        const int64_t base = (int64_t)begin + 64 * (int64_t)t;
+        if (base >= end) break;
+        const int ka = (int)base + (int)lane, kb = ka + 32;
+        const bool va = ka < end, vb = kb < end;
+        EvalBody A, B;
+        unsigned vma, vmb;
+        {
+            const float4 pa = va ? posm[ka] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 pb = vb ? posm[kb] : make_float4(0.f, 0.f, 0.f, 0.f);
+            A.npx = -pa.x; A.npy = -pa.y; A.npz = -pa.z;
+            B.npx = -pb.x; B.npy = -pb.y; B.npz = -pb.z;
+            vma = __ballot_sync(0xffffffffu, va);
+            vmb = __ballot_sync(0xffffffffu, vb);
+            // boxes of the two halves (over their valid bodies)
+            const int big = 0x7f7fffff;   // f2ord(FLT_MAX)
+            int lo[6], hi[6];
+            const float pv[6] = {pa.x, pa.y, pa.z, pb.x, pb.y, pb.z};
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const bool v = q < 3 ? va : vb;
+                const int o = f2ord(pv[q]);
+                lo[q] = __reduce_min_sync(0xffffffffu, v ? o : big);
+                hi[q] = __reduce_max_sync(0xffffffffu, v ? o : -big);
+            }
+            if (lane == 0) {
+                ws.box[0] = make_float4(ord2f(lo[0]), ord2f(lo[1]), ord2f(lo[2]), 0.f);
+                ws.box[1] = make_float4(ord2f(hi[0]), ord2f(hi[1]), ord2f(hi[2]), 0.f);
+                ws.box[2] = make_float4(ord2f(lo[3]), ord2f(lo[4]), ord2f(lo[5]), 0.f);
+                ws.box[3] = make_float4(ord2f(hi[3]), ord2f(hi[4]), ord2f(hi[5]), 0.f);
+                ws.stk_first[0] = 0u; ws.stk_lo[0] = vma; ws.stk_hi[0] = vmb;   // pair 0 = {root, dummy}
+            }
+        }
+        A.ax = A.ay = A.az = B.ax = B.ay = B.az = make_float2(0.f, 0.f);
+        A.cnt = A.lanepairs = B.cnt = B.lanepairs = 0;
+        int slots_a = 0, slots_b = 0;
+        int sp = 1;
+        __syncwarp();
+        while (sp > 0) {
+            // ---- select: the top entries, one per lane
+            const int idx = sp - 1 - (int)lane;
+            unsigned ef = 0, ml = 0, mh = 0;
+            if (idx >= 0) { ef = ws.stk_first[idx]; ml = ws.stk_lo[idx]; mh = ws.stk_hi[idx]; }
+            const unsigned multi = __ballot_sync(0xffffffffu, (ef >> 29) != 0u);
+            const bool chunk = (multi & 1u) != 0u;
+            const int room = (TRAV_CAP - TRAV_RESERVE - sp) / 7;
+            int E = min(min(sp, TRAV_BATCH), max(room, 1));
+            if (multi) E = min(E, __ffs(multi) - 1);
+            int P = E;
+            if (chunk) {   // a chunk of a bucket is a batch of its own: P consecutive pairs with the entry's masks
+                const unsigned ef0 = __shfl_sync(0xffffffffu, ef, 0);
+                ml = __shfl_sync(0xffffffffu, ml, 0);
+                mh = __shfl_sync(0xffffffffu, mh, 0);
+                E = 1;
+                P = (int)(ef0 >> 29) + 1;
+                ef = (ef0 & TRAV_FIRST_MASK) + lane;
+            }
+            P = __reduce_max_sync(0xffffffffu, P);
+            sp -= E;
+            // ---- load + classify: lane j owns pair slot j
+            const bool mine = (int)lane < P;
+            int cls = 5;   // 0 FF, 1 SS, 2 SA, 3 SB, 4 UU, 5 none
+            float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0, q3 = q0;
+            if (mine) {
+                const float4* r = recs + 4 * (int64_t)(ef & TRAV_FIRST_MASK);
+                q0 = __ldg(r); q1 = __ldg(r + 1); q2 = __ldg(r + 2); q3 = __ldg(r + 3);
+                const float T0 = q2.x * TRAV_SURE_MARGIN, T1 = q2.y * TRAV_SURE_MARGIN;
+                bool sureA = true, sureB = true;
+                if (ml) {
+                    const float4 blo = ws.box[0], bhi = ws.box[1];
+                    float2 m2 = box_axis(make_float2(q0.x, q0.y), blo.x, bhi.x, eps22);
+                    m2 = box_axis(make_float2(q0.z, q0.w), blo.y, bhi.y, m2);
+                    m2 = box_axis(make_float2(q1.x, q1.y), blo.z, bhi.z, m2);
+                    sureA = m2.x > T0 && m2.y > T1;
+                }
+                if (mh) {
+                    const float4 blo = ws.box[2], bhi = ws.box[3];
+                    float2 m2 = box_axis(make_float2(q0.x, q0.y), blo.x, bhi.x, eps22);
+                    m2 = box_axis(make_float2(q0.z, q0.w), blo.y, bhi.y, m2);
+                    m2 = box_axis(make_float2(q1.x, q1.y), blo.z, bhi.z, m2);
+                    sureB = m2.x > T0 && m2.y > T1;
+                }
+                if (eps2 <= 0.f) sureA = sureB = false;   // a body's own leaf must go through the MAC's d2 > eps2 test
+                if (!(sureA && sureB)) cls = 4;
+                else if (ml && mh) cls = (ml == vma && mh == vmb) ? 0 : 1;
+                else cls = ml ? 2 : 3;
+            }
+            const unsigned b0 = __ballot_sync(0xffffffffu, cls == 0), b1 = __ballot_sync(0xffffffffu, cls == 1);
+            const unsigned b2 = __ballot_sync(0xffffffffu, cls == 2), b3 = __ballot_sync(0xffffffffu, cls == 3);
+            const unsigned b4 = __ballot_sync(0xffffffffu, cls == 4);
+            const int n0 = __popc(b0), n1 = n0 + __popc(b1), n2 = n1 + __popc(b2), n3 = n2 + __popc(b3);
+            const unsigned mycls = cls == 0 ? b0 : cls == 1 ? b1 : cls == 2 ? b2 : cls == 3 ? b3 : b4;
+            const int cbase = cls == 0 ? 0 : cls == 1 ? n0 : cls == 2 ? n1 : cls == 3 ? n2 : n3;
+            const int pos = cbase + __popc(mycls & lt);
+            if (mine) {
+                sXY[pos] = q0;
+                sZM[pos] = q1;
+                sTM[pos] = make_float4(q2.x, q2.y, __uint_as_float(ml), __uint_as_float(mh));
+                sFN[lane] = q3;
+            }
+            __syncwarp();
+            // ---- eval, one loop per class (warp-uniform trip counts)
+            const int e0 = n0, e1 = n1, e2 = n2, e3 = n3;
+#pragma unroll 2
+            for (int j = 0; j < e0; ++j) {
+                const float4 XY = sXY[j];
+                const float4 ZM = sZM[j];
+                eval_sure<COUNT, 2>(XY, ZM, va, eps22, A);   // (va / vb only matter to the counters of a ragged last tile)
+                eval_sure<COUNT, 2>(XY, ZM, vb, eps22, B);
+            }
+#pragma unroll 2
+            for (int j = e0; j < e1; ++j) {
+                const float4 XY = sXY[j];
+                const float4 ZM = sZM[j];
+                const float4 TM = sTM[j];
+                eval_sure<COUNT, 1>(XY, ZM, (__float_as_uint(TM.z) & lanebit) != 0u, eps22, A);
+                eval_sure<COUNT, 1>(XY, ZM, (__float_as_uint(TM.w) & lanebit) != 0u, eps22, B);
+            }
+#pragma unroll 2
+            for (int j = e1; j < e2; ++j) {
+                const float4 XY = sXY[j];
+                const float4 ZM = sZM[j];
+                const float4 TM = sTM[j];
+                eval_sure<COUNT, 1>(XY, ZM, (__float_as_uint(TM.z) & lanebit) != 0u, eps22, A);
+            }
+#pragma unroll 2
+            for (int j = e2; j < e3; ++j) {
+                const float4 XY = sXY[j];
+                const float4 ZM = sZM[j];
+                const float4 TM = sTM[j];
+                eval_sure<COUNT, 1>(XY, ZM, (__float_as_uint(TM.w) & lanebit) != 0u, eps22, B);
+            }
+#pragma unroll 2
+            for (int j = e3; j < P; ++j) {
+                const float4 XY = sXY[j];
+                const float4 ZM = sZM[j];
+                const float4 TM = sTM[j];
+                uint4 om;
+                eval_pair<COUNT>(XY, ZM, TM.x, TM.y, __float_as_uint(TM.z), lanebit, eps22, A, om.x, om.y);
+                eval_pair<COUNT>(XY, ZM, TM.x, TM.y, __float_as_uint(TM.w), lanebit, eps22, B, om.z, om.w);
+                if (lane == 0) sOP[j] = om;
+            }
+            if (COUNT) {
+                // UU pairs: count the halves that are really needed (masks non-empty), like the class-sorted walk
+                const unsigned ua = __ballot_sync(0xffffffffu, cls == 4 && ml != 0u), ub = __ballot_sync(0xffffffffu, cls == 4 && mh != 0u);
+                slots_a += e2 + __popc(ua);
+                slots_b += e1 + (e3 - e2) + __popc(ub);
+                w_both += (unsigned)(e1 + __popc(ua & ub));
+                w_sure += (unsigned)(e1 + e3);   // (pair, half) evaluations that skipped the MAC: FF and SS count twice
+            } else {   // cost proxy for the sharding: evaluated (pair, half) slots
+                slots_a += e2 + (P - e3);
+                slots_b += e1 + (e3 - e2) + (P - e3);
+            }
+            __syncwarp();
+            // ---- expand: only UU pairs can have opened children
+            unsigned f0 = 0, f1 = 0, c0n = 0, c1n = 0;
+            uint4 om = make_uint4(0u, 0u, 0u, 0u);
+            if (cls == 4) {
+                om = sOP[pos];
+                om.x &= ml; om.y &= ml; om.z &= mh; om.w &= mh;   // the ballots include the lanes outside the masks
+                const float4 fn = sFN[lane];
+                f0 = __float_as_uint(fn.x); f1 = __float_as_uint(fn.y);
+                c0n = __float_as_uint(fn.z); c1n = __float_as_uint(fn.w);
+            }
+            const bool c0 = (om.x | om.z) != 0u && c0n != 0u, c1 = (om.y | om.w) != 0u && c1n != 0u;
+            const int np0 = c0 ? (int)((c0n + 1u) >> 1) : 0, np1 = c1 ? (int)((c1n + 1u) >> 1) : 0;
+            const bool bigc = np0 > TRAV_CELL_PAIRS || np1 > TRAV_CELL_PAIRS;
+            if (!__any_sync(0xffffffffu, bigc)) {
+                const unsigned k = (unsigned)(np0 + np1);
+                const unsigned k0 = __ballot_sync(0xffffffffu, (k & 1u) != 0u), k1 = __ballot_sync(0xffffffffu, (k & 2u) != 0u);
+                const unsigned k2 = __ballot_sync(0xffffffffu, (k & 4u) != 0u), k3 = __ballot_sync(0xffffffffu, (k & 8u) != 0u);
+                const int total = __popc(k0) + 2 * __popc(k1) + 4 * __popc(k2) + 8 * __popc(k3);
+                if (sp + total > TRAV_CAP) {   // cannot happen (see the stack bound above); never drop silently
+                    if (lane == 0) atomicOr(error, (unsigned)ERR_STACK_OVERFLOW);
+                    sp = 0;
+                } else {
+                    int p = sp + __popc(k0 & lt) + 2 * __popc(k1 & lt) + 4 * __popc(k2 & lt) + 8 * __popc(k3 & lt);
+                    for (int q = 0; q < np0; ++q, ++p) { ws.stk_first[p] = f0 + (unsigned)q; ws.stk_lo[p] = om.x; ws.stk_hi[p] = om.z; }
+                    for (int q = 0; q < np1; ++q, ++p) { ws.stk_first[p] = f1 + (unsigned)q; ws.stk_lo[p] = om.y; ws.stk_hi[p] = om.w; }
+                    sp += total;
+                }
+            } else {
+                // rare: a bucket of > 8 bodies sharing one finest-level cell is pushed in chunks of <= 8 pairs
+                const int x0 = (np0 + TRAV_CHUNK_PAIRS - 1) / TRAV_CHUNK_PAIRS;
+                const int x1 = (np1 + TRAV_CHUNK_PAIRS - 1) / TRAV_CHUNK_PAIRS;
+                int inc2 = x0 + x1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, inc2, o);
+                    if ((int)lane >= o) inc2 += u;
+                }
+                const int total = __reduce_add_sync(0xffffffffu, x0 + x1);
+                if (sp + total > TRAV_CAP) {   // never drop silently
+                    if (lane == 0) atomicOr(error, (unsigned)ERR_STACK_OVERFLOW);
+                    sp = 0;
+                } else {
+                    int p = sp + inc2 - (x0 + x1);
+                    for (int q = 0; q < x0; ++q, ++p) {
+                        const int r = min(np0 - TRAV_CHUNK_PAIRS * q, TRAV_CHUNK_PAIRS);
+                        ws.stk_first[p] = (f0 + (unsigned)(TRAV_CHUNK_PAIRS * q)) | ((unsigned)(r - 1) << 29);
+                        ws.stk_lo[p] = om.x; ws.stk_hi[p] = om.z;
+                    }
+                    for (int q = 0; q < x1; ++q, ++p) {
+                        const int r = min(np1 - TRAV_CHUNK_PAIRS * q, TRAV_CHUNK_PAIRS);
+                        ws.stk_first[p] = (f1 + (unsigned)(TRAV_CHUNK_PAIRS * q)) | ((unsigned)(r - 1) << 29);
+                        ws.stk_lo[p] = om.y; ws.stk_hi[p] = om.w;
+                    }
+                    sp += total;
+                }
+            }
+            sp = __reduce_max_sync(0xffffffffu, sp);   // uniform register: the walk loop is provably convergent
+            if (COUNT) { ++w_batches; w_spmax = max(w_spmax, sp); }
+            __syncwarp();
+        }
+        // acc.w: exact interaction count (COUNT) or the half-tile's evaluated pair slots (a cost proxy)
+        if (va) acc[ka] = make_float4(G * (A.ax.x + A.ax.y), G * (A.ay.x + A.ay.y), G * (A.az.x + A.az.y), __int_as_float(COUNT ? A.cnt : slots_a));
+        if (vb) acc[kb] = make_float4(G * (B.ax.x + B.ax.y), G * (B.ay.x + B.ay.y), G * (B.az.x + B.az.y), __int_as_float(COUNT ? B.cnt : slots_b));
+        if (COUNT) {
+            unsigned c32 = (va ? (unsigned)A.cnt : 0u) + (vb ? (unsigned)B.cnt : 0u), l32 = (unsigned)(A.lanepairs + B.lanepairs);
+            for (int o = 16; o > 0; o >>= 1) {
+                c32 += __shfl_xor_sync(0xffffffffu, c32, o);
+                l32 += __shfl_xor_sync(0xffffffffu, l32, o);
+            }
+            w_inter += c32;
+            w_lanepairs += l32;
+            w_slots += (unsigned)(slots_a + slots_b);
+        }
+    }
+    if (COUNT && lane == 0) {
+        if (w_inter) atomicAdd(&counters[0], w_inter);
+        atomicAdd(&counters[1], w_slots);
+        atomicAdd(&counters[2], w_lanepairs);
+        atomicAdd(&counters[3], w_batches);
+        atomicMax(&counters[4], (unsigned long long)w_spmax);
+        atomicAdd(&counters[5], w_both);
+        atomicAdd(&counters[6], w_sure);
+    }
+}

@@ -1,7 +1,11 @@
 """Run the reference's own tools against the B200 backend, unchanged.
 
     python -m b200sim.dropin --reference-root /path/to/reference record --preset quick_galaxy
+    python -m b200sim.dropin --reference-root /path/to/reference --seed 0 record --preset tiny_galaxy --frames 6
     python -m b200sim.dropin --reference-root /path/to/reference nbody_main
+
+``--seed S`` calls ``numpy.random.seed(S)`` before the tool starts: the reference's generators draw from
+numpy's global RandomState (tools/presets.py:91-1390) and are otherwise unseeded.
 
 ``install()`` puts the reference checkout on ``sys.path`` and registers this package's
 ``nbody.gpu_backend`` under the reference's module name, so ``from nbody.gpu_backend import
@@ -107,13 +111,21 @@ def install(reference_root: str, headless: bool = True):
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     root = os.environ.get("B200SIM_REFERENCE_ROOT", "/root/reference")
-    if argv and argv[0] == "--reference-root":
-        root, argv = argv[1], argv[2:]
+    seed = None
+    while argv and argv[0] in ("--reference-root", "--seed"):
+        if argv[0] == "--reference-root":
+            root = argv[1]
+        else:
+            seed = int(argv[1])
+        argv = argv[2:]
     if not argv:
         print(__doc__)
         return 2
     tool, rest = argv[0], argv[1:]
     install(root)
+    if seed is not None:
+        import numpy as np
+        np.random.seed(seed)
     sys.argv = [tool] + rest
     if tool == "record":
         return importlib.import_module("tools.record").main()

@@ -260,6 +260,19 @@ class B200BarnesHutSimulation:
         _lib.check(self._L.b200_nbody_timed_steps(self._handle(), float(dt), int(nsteps), C.byref(ms)))
         return float(ms.value)
 
+    def count_interactions(self) -> int:
+        """Accepted interactions of one force pass over this handle's shard on the current state
+        (nothing integrated): the count the timed traversal of the NEXT step() works through."""
+        v = C.c_int64(0)
+        _lib.check(self._L.b200_nbody_count_interactions(self._handle(), C.byref(v)))
+        return int(v.value)
+
+    def state_checksum(self):
+        """(positions, velocities) 64-bit checksums keyed by creation index: equal iff bit-identical states."""
+        out = (C.c_uint64 * 2)()
+        _lib.check(self._L.b200_nbody_state_checksum(self._handle(), out))
+        return int(out[0]), int(out[1])
+
     def launch_count(self) -> int:
         v = C.c_int64(0)
         _lib.check(self._L.b200_nbody_launch_count(self._handle(), C.byref(v)))

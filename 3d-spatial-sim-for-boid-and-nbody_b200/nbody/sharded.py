@@ -99,6 +99,11 @@ class ShardedSimulation:
         self.sim.step_end(dt)
         self._in_morton_order = True
 
+    def shard_bodies(self) -> int:
+        """Bodies this rank traverses (and sorts, with the sharded sort)."""
+        b, e = partition_equal(self.n, self.world)[self.rank]
+        return e - b
+
     # a new state arrives in creation order: the next step must sort everything
     def set_state(self, positions, velocities):
         self._in_morton_order = False

@@ -12,8 +12,11 @@ is measured in the same run at N=1 and reported under "also".  Inputs are synthe
 generated on the host and resident in HBM before the timed region; per-step touched data is
 far larger than the 126 MB L2 at both sizes (no L2 flush needed).
 
-Prints ONE JSON line on rank 0.  `--impl reference` times the reference's CPU path
-(the oracle port of its Numba kernels, all host cores) on the same config.
+Prints ONE JSON line on rank 0.  `--impl reference` times the reference's own CPU path on the same
+config: its unmodified Numba kernels (nbody/simulation.py:63-317) imported from oracle/_ref and sequenced
+exactly as tools/record.py:835-858, on all host cores, over a bounded sample (the first 1 M bodies of the
+workload, the same sample `cpu_baseline` in the GPU arm uses); the C/OpenMP port of those kernels
+(oracle/) is the fallback when the reference tree did not travel.
 """
 from __future__ import annotations
 
@@ -121,53 +124,177 @@ def _workload(key: str, bodies: int | None):
 
 
 # ----------------------------------------------------------------------------- CPU baseline
-def cpu_step_sample(cfg, pos, vel, mass, sample: int):
-    """One full oracle substep (tools/record.py:835-858 sequence) on the first `sample` bodies."""
-    from oracle import oracle as orc
-    n = min(sample, len(pos))
-    p, v, m = pos[:n].copy(), vel[:n].copy(), mass[:n].copy()
-    t0 = time.perf_counter()
-    orc.nbody_step(p, v, m, cfg["theta"], cfg["G"], cfg["softening"], cfg["damping"], cfg["dt"])
-    return n, time.perf_counter() - t0
+def _host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
-def cpu_baseline(cfg, pos, vel, mass, reps: int = 1):
-    from oracle import oracle as orc
-    best, n = None, 0
-    for _ in range(reps):
-        n, t = cpu_step_sample(cfg, pos, vel, mass, CPU_SAMPLE_BODIES)
-        best = t if best is None else min(best, t)
-    return {"value": n / best, "unit": "body-updates/s", "cores": orc.num_threads(), "kind": "port",
-            "sample": f"one full oracle substep (bounds, sequential octree build, BH forces on all cores, "
-                      f"integrate) on the first {n:,} bodies of the workload; {best:.2f} s"}
+def _cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    import platform
+    return platform.processor() or "unknown"
+
+
+def _pin_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1: the CPU arm must not inherit it.  Must run before numba is imported."""
+    t = str(_host_threads())
+    os.environ["NUMBA_NUM_THREADS"] = t
+    os.environ["OMP_NUM_THREADS"] = t
+    os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/b200sim_numba_cache")
+
+
+class CpuPath:
+    """The reference's CPU substep on a bounded sample: kind 'reference' = the unmodified Numba kernels from
+    oracle/_ref called as tools/record.py:835-858 does (arrays sized as :795-803); kind 'port' = the oracle's C/OpenMP
+    restatement.  step() returns seconds spent in (bounds + pool reset, build, forces, integrate)."""
+
+    def __init__(self, cfg, pos, vel, mass):
+        _pin_host_threads()
+        self.cfg = cfg
+        self.n = len(pos)
+        self.p, self.v, self.m = pos.copy(), vel.copy(), mass.copy()
+        self.kind, self.info = "port", {}
+        self.ref = None
+        try:
+            from oracle import refimport
+            if refimport.available():
+                self.ref = refimport.load()
+                import numba
+                numba.set_num_threads(min(_host_threads(), numba.config.NUMBA_NUM_THREADS))
+                self.kind = "reference"
+                self.info = {"numba": numba.__version__, "numba_threads": numba.get_num_threads(),
+                             "reference_root": os.path.relpath(refimport.REFERENCE_ROOT, ROOT)}
+        except Exception as e:   # numba missing / tree unreadable: the port still runs
+            self.ref, self.kind, self.info = None, "port", {"reference_unavailable": repr(e)[:200]}
+        from oracle import oracle as orc
+        self.orc = orc
+        if self.ref is None:
+            orc.build()
+            orc.set_num_threads(_host_threads())
+            self.cores = orc.num_threads()
+        else:
+            self.cores = self.info["numba_threads"]
+            n = self.n
+            mx = min(8_000_000, n * 4)                              # tools/record.py:795
+            self.nc, self.nh = np.zeros((mx, 3)), np.zeros(mx)
+            self.nm, self.ncom = np.zeros(mx), np.zeros((mx, 3))
+            self.nch, self.nb = np.full((mx, 8), -1, np.int32), np.full(mx, -1, np.int32)
+            self.leaf = np.ones(mx, np.bool_)
+            self.acc = np.zeros((n, 3))
+
+    def step(self):
+        c, n = self.cfg, self.n
+        t = [time.perf_counter()]
+        if self.ref is not None:
+            r = self.ref
+            bounds = r.compute_bounds(self.p, n)
+            self.nch.fill(-1); self.nb.fill(-1); self.leaf.fill(True)
+            t.append(time.perf_counter())
+            nn = r.build_octree(self.p, self.m, n, bounds, self.nc, self.nh, self.nm, self.ncom, self.nch, self.nb, self.leaf)
+            t.append(time.perf_counter())
+            r.compute_forces_barnes_hut(self.p, self.m, self.acc, self.nc, self.nh, self.nm, self.ncom, self.nch, self.nb,
+                                        self.leaf, nn, n, c["theta"], c["G"], c["softening"])
+            t.append(time.perf_counter())
+            r.update_positions_velocities(self.p, self.v, self.acc, c["damping"], c["dt"], n)
+            t.append(time.perf_counter())
+        else:
+            o = self.orc
+            bounds = o.compute_bounds(self.p)
+            t.append(time.perf_counter())
+            tree = o.build_octree(self.p, self.m, bounds)
+            t.append(time.perf_counter())
+            acc = o.compute_forces(self.p, tree, c["theta"], c["G"], c["softening"])
+            t.append(time.perf_counter())
+            o.update(self.p, self.v, acc, c["damping"], c["dt"])
+            t.append(time.perf_counter())
+        return [t[i + 1] - t[i] for i in range(4)]
+
+    def threading_layer(self):
+        if self.ref is None:
+            return "openmp"
+        try:
+            import numba
+            return numba.threading_layer()
+        except Exception:
+            return "unknown"
+
+
+def _cpu_sample(pos, vel, mass):
+    """The bounded CPU sample: the first CPU_SAMPLE_BODIES bodies of the workload (creation order is i.i.d.,
+    so this is the same distribution at 1/50 of the density).  Both arms use exactly these rows."""
+    n = min(CPU_SAMPLE_BODIES, len(pos))
+    return pos[:n], vel[:n], mass[:n]
+
+
+def _cpu_line(path: "CpuPath", times, full_bodies):
+    """times: list of [prep, build, forces, integrate] seconds per step."""
+    tot = [sum(t) for t in times]
+    n = path.n
+    best = min(tot)
+    value = n / best
+    split = {k: float(np.median([t[i] for t in times])) for i, k in enumerate(("bounds_and_reset_s", "build_s", "forces_s", "integrate_s"))}
+    import math
+    out = {"value": value, "unit": "body-updates/s", "cores": path.cores, "kind": path.kind,
+           "sample": f"one full substep of the {'reference Numba kernels (oracle/_ref, tools/record.py:835-858 sequence)' if path.kind == 'reference' else 'oracle C/OpenMP port of the reference kernels'}"
+                     f" on the first {n:,} bodies of the workload; best of {len(times)}: {best:.2f} s",
+           "split_median": split, "cpu_model": _cpu_model(), "host_threads": _host_threads(), "threading_layer": path.threading_layer(),
+           "note": "build_octree is sequential by construction (nbody/simulation.py:63-198); forces run on all cores (prange :225)"}
+    out.update(path.info)
+    if full_bodies > n:
+        out["extrapolated_full_size_value"] = value * math.log(n) / math.log(full_bodies)
+        out["extrapolation"] = (f"N log N scaling from {n:,} to {full_bodies:,} bodies (value x ln n / ln N); the reference itself cannot run "
+                                "this size correctly (8 M-node cap drops bodies above ~5.4 M, 64-entry stack: SURVEY section 0)")
+    return out
+
+
+def cpu_baseline(cfg, pos, vel, mass, reps: int = 2):
+    sp, sv, sm = _cpu_sample(pos, vel, mass)
+    path = CpuPath(cfg, sp, sv, sm)
+    if path.kind == "reference":
+        path.step()                                    # JIT compile + first-touch (untimed)
+    times = [path.step() for _ in range(reps)]
+    return _cpu_line(path, times, len(pos))
 
 
 def run_reference(args):
     rank, _local, world = _dist_env()
     if rank != 0:
         return 0
+    _pin_host_threads()
     key = args.workload or "extreme_50m_galaxy_t07"
-    from oracle import oracle as orc
-    orc.build()
-    cfg, pos, vel, mass, _ = _workload(key, min(args.bodies or 10 ** 12, CPU_SAMPLE_BODIES))
-    for _ in range(min(args.warmup, 1)):          # no JIT to warm: one touch is enough
-        cpu_step_sample(cfg, pos, vel, mass, CPU_SAMPLE_BODIES)
-    times, n = [], len(pos)
-    for _ in range(args.steps):
-        n, t = cpu_step_sample(cfg, pos, vel, mass, CPU_SAMPLE_BODIES)
-        times.append(t)
-    total = sum(times)
-    value = n * len(times) / total
+    cfg, pos, vel, mass, _ = _workload(key, args.bodies)
+    full = len(pos)
+    sp, sv, sm = _cpu_sample(pos, vel, mass)
+    del pos, vel, mass
+    path = CpuPath(cfg, sp, sv, sm)
+    for _ in range(max(1, min(args.warmup, 2)) if path.kind == "reference" else min(args.warmup, 1)):
+        path.step()                                    # Numba JIT + first touch
+    steps = max(1, min(args.steps, 10))                # bounded: a substep on the sample takes seconds
+    times = [path.step() for _ in range(steps)]
+    total = sum(sum(t) for t in times)
+    n = path.n
+    value = n * steps / total
+    cb = _cpu_line(path, times, full)
+    cb["value"] = value
     line = {
         "impl": "reference", "metric": "body_updates_per_sec", "value": value, "unit": "body-updates/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": key, "bodies": cfg["num_bodies"], "theta": cfg["theta"], "G": cfg["G"],
-                   "softening": cfg["softening"], "dt": cfg["dt"], "sample_bodies": n},
-        "cpu_baseline": {"value": value, "unit": "body-updates/s", "cores": orc.num_threads(), "kind": "port",
-                         "sample": f"each step = one full oracle substep on a {n:,}-body sample of the workload "
-                                   "(the reference's Numba path cannot travel to the GPU box; its 8 M-node cap also "
-                                   "makes it invalid above ~5.4 M bodies)"},
+        "config": {"workload": key, "bodies": full, "theta": cfg["theta"], "G": cfg["G"],
+                   "softening": cfg["softening"], "dt": cfg["dt"], "distribution": cfg["distribution"], "seed": 0,
+                   "sample_bodies": n,
+                   "same_config": "same workload, parameters and seed as the GPU arm; each step is one full CPU substep on a bounded "
+                                  f"sample (the first {n:,} of the {full:,} bodies -- the rows cpu_baseline in the GPU arm uses): the "
+                                  "reference cannot hold the full size (8 M-node cap) and a full-size CPU step would take minutes"},
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "body-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -221,19 +348,38 @@ def _measure_boids(args, torch, peaks):
         f.get_state(out=outs)
     el = time.perf_counter() - t0
     f.close()
-    p, v, c = pos0, vel0, col0
-    orc.boids_step(p, v, c, dt)                    # touch
-    t0 = time.perf_counter()
-    orc.boids_step(p, v, c, dt)
-    cpu_s = time.perf_counter() - t0
+    _pin_host_threads()
+    kind, cores, cpu_s = "port", None, None
+    try:
+        from oracle import refimport
+        if refimport.available():
+            ref = refimport.load()
+            import numba
+            rf = ref.Flock(n)                                       # boids/flock.py:459 (config defaults)
+            rf.positions[:], rf.velocities[:], rf.colors[:] = pos0, vel0, col0
+            rf.update(dt)                                           # JIT + first touch
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter(); rf.update(dt); ts.append(time.perf_counter() - t0)
+            cpu_s, kind, cores = float(np.median(ts)), "reference", numba.get_num_threads()
+    except Exception:
+        kind = "port"
+    if kind == "port":
+        orc.set_num_threads(_host_threads())
+        p, v, c = pos0, vel0, col0
+        orc.boids_step(p, v, c, dt)                    # touch
+        t0 = time.perf_counter()
+        orc.boids_step(p, v, c, dt)
+        cpu_s, cores = time.perf_counter() - t0, orc.num_threads()
     return {"workload": "boids_flock_1m", "boids": n, "dt": dt, "value": n / (ms_uniform * 1e-3), "unit": "boid-updates/s",
             "ms_per_step": ms_uniform, "ms_per_step_after_500_steps": ms_clustered,
             "value_after_500_steps": n / (ms_clustered * 1e-3), "neighbour_pairs_per_boid": pairs, "phases": phases,
             "dtype": "f64", "grid": {"dim": st["grid_dim"], "cells": st["num_cells"], "key_bits": st["key_bits"]},
             "e2e": {"value": n * e2e_steps / el, "unit": "boid-updates/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 72 * n, "what": "B200Flock.update + get_state(pos, vel, col) into pinned host buffers"},
-            "cpu_baseline": {"value": n / cpu_s, "unit": "boid-updates/s", "cores": orc.num_threads(), "kind": "port",
-                             "sample": f"one oracle Flock.update on the same 1,000,000-boid initial state; {cpu_s:.2f} s"}}
+            "cpu_baseline": {"value": n / cpu_s, "unit": "boid-updates/s", "cores": cores, "kind": kind, "cpu_model": _cpu_model(),
+                             "sample": f"one Flock.update ({'reference boids/flock.py:627-678, Numba' if kind == 'reference' else 'oracle C/OpenMP port'}) "
+                                       f"on the same 1,000,000-boid initial state; {cpu_s:.3f} s"}}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -287,34 +433,52 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
     ms_per_step = ms_total / args.steps
     value = n / (ms_per_step * 1e-3)
 
-    # ---- per-phase device times (CUDA events inside the library, same stream), separate pass
+    # ---- per-phase device times (CUDA events inside the library, same stream), separate pass.  Before every
+    # profiled step a counting force pass runs on the SAME state (nothing integrated), so the interactions the
+    # roofline divides by are exactly those of the traversals that were timed.
     sim.reset_stats()
     sim.set_profiling(True)
+    inter_local = 0
     for _ in range(args.steps):
+        sim.set_profiling(False)
+        inter_local += sim.count_interactions()
+        sim.set_profiling(True)
         sh.step(dt)
     torch.cuda.synchronize()
     st = sim.get_stats()
-    phase = {k: v / max(st["timed_steps"], 1) for k, v in st["phase_ms"].items()}
-    # interactions per step: a short counting pass (exact device-side counters cost a few
-    # instructions per child, so the timed passes above run without them)
-    sim.reset_stats()
-    sim.set_counting(True)
-    count_steps = 2
-    for _ in range(count_steps):
-        sh.step(dt)
-    torch.cuda.synchronize()
-    cst = sim.get_stats()
-    sim.set_counting(False)
     sim.set_profiling(False)
-    inter = torch.tensor([float(cst["interactions"]) / count_steps], device="cuda", dtype=torch.float64)
+    phase = {k: v / max(st["timed_steps"], 1) for k, v in st["phase_ms"].items()}
+    inter = torch.tensor([float(inter_local) / args.steps], device="cuda", dtype=torch.float64)
     trav = torch.tensor([phase["traverse"]], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(inter, op=dist.ReduceOp.SUM)
         dist.all_reduce(trav, op=dist.ReduceOp.MAX)
     inter_step, trav_ms = float(inter.item()), float(trav.item())
 
+    # ---- replicas (N > 1): every rank's state against rank 0's, and against an unsharded replay of the same
+    # number of steps from the same initial state on rank 0's GPU
+    replicas = None
+    if world > 1:
+        steps_done = st["steps"]
+        cs = torch.tensor([c & 0x7fffffffffffffff for c in sim.state_checksum()], device="cuda", dtype=torch.int64)
+        allcs = [torch.zeros_like(cs) for _ in range(world)]
+        dist.all_gather(allcs, cs)
+        same = all(bool(torch.equal(allcs[0], c)) for c in allcs)
+        replay = None
+        if rank == 0:
+            from b200sim.nbody.gpu_backend import B200BarnesHutSimulation
+            twin = B200BarnesHutSimulation(pos, vel, mass, cfg["G"], cfg["softening"], cfg["damping"], cfg["theta"], device=local)
+            twin.step_n(dt, int(steps_done))
+            tc = [c & 0x7fffffffffffffff for c in twin.state_checksum()]
+            replay = tc == [int(x) for x in allcs[0].tolist()]
+            twin.close()
+        replicas = {"replicas_identical": same, "matches_single_gpu_replay": replay, "steps_compared": int(steps_done),
+                    "how": "64-bit checksums of the fp64 positions and velocities keyed by creation index (b200_nbody_state_checksum), "
+                           "all-gathered; rank 0 replays the same steps unsharded on its own GPU"}
+
     out = dict(cfg=cfg, n=n, gen_s=gen_s, ms_per_step=ms_per_step, value=value, launches=launches, clocks=clocks,
-               phase=phase, inter_step=inter_step, trav_ms=trav_ms, stats=st, pos=pos, vel=vel, mass=mass)
+               phase=phase, inter_step=inter_step, trav_ms=trav_ms, stats=st, pos=pos, vel=vel, mass=mass, replicas=replicas,
+               shard_bodies=sh.shard_bodies())
 
     # ---- end to end through the public API with HOST buffers, inside the timed region every step:
     # H2D of the step's inputs (48 B/body, pinned) + step + colours + D2H of positions and colours
@@ -395,6 +559,15 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
                 sim.frame_delta_begin(15.0, out_dp[i & 1], out_dc[i & 1])
             sim.frame_wait()
 
+        def run_recorder_loop(k):
+            # what tools/record.py:818-832 does per frame with substeps = 1: step, colours, positions and colours to
+            # the host; the state stays on the device (no upload), the read-back overlaps the next step
+            for i in range(k):
+                sh.step(dt)
+                sh.frame_wait()
+                sh.frame_begin(15.0, out_p[i & 1], out_c[i & 1])
+            sh.frame_wait()
+
         def timed(fn):
             fn(1)
             if world > 1:
@@ -417,6 +590,7 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
             dist.all_reduce(el, op=dist.ReduceOp.MAX)
         v_steady = n * steady_steps / float(el.item())
         v_delta = timed(run_pipelined_delta) if world == 1 else None
+        v_rec = timed(run_recorder_loop)
         out["e2e"] = {"value": v_steady, "unit": "body-updates/s", "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 24 * n,
                       "steps": steady_steps,
                       "pipeline": "steady state: timed with the pipeline full (one untimed prologue iteration); every timed "
@@ -429,6 +603,9 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
                       "delta_frames_value": v_delta,
                       "delta_frames_what": "same loop with frame_delta_begin (the recorder's int16 delta payload, computed on the "
                                            "device): 12 B/body device-to-host per step instead of 24",
+                      "recorder_loop_value": v_rec,
+                      "recorder_loop_what": "the reference recorder's own frame loop (tools/record.py:818-832, substeps 1): step + frame "
+                                            "egress (24 B/body device-to-host) every step, no upload -- the state lives on the device",
                       "blocking_value": v_block,
                       "blocking_what": "same bytes with the reference-style blocking calls: set_state + step + compute_colors + "
                                        "get_positions + get_colors"}
@@ -460,8 +637,9 @@ def run_gpu(args):
     peaks, peak_src = _peaks()
     fp32_peak = _lib.fp32_peak_tflops(local)
     achieved = FLOP_PER_INTERACTION * m["inter_step"] / (m["trav_ms"] * 1e-3) / 1e12 / world   # per GPU
+    kernel = "traverse64_kernel" if m["stats"].get("trav_kernel") == 64 else "traverse_kernel"
     roofline = {
-        "kernel": "traverse_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+        "kernel": kernel, "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
         "frac": achieved / fp32_peak if fp32_peak else None,
         "traffic": (_traffic(key, "traverse") if world == 1 and n == cfg["num_bodies"] else None),
         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r01_traffic.json); "
@@ -470,26 +648,38 @@ def run_gpu(args):
                        "MEASURED_PEAKS.json has no FP32 entry; nominal 148 SM x 128 x 2 x 1.965 GHz = 74.4",
         "algorithmic_flop_per_launch": FLOP_PER_INTERACTION * m["inter_step"] / world,
         "interactions_per_body": m["inter_step"] / n, "launch_ms": m["trav_ms"],
+        "interactions_counted": "on the same states as the timed traversals (a counting pass before every profiled step)",
+        "ceiling": "exact per-body MAC bounds this kernel at ~0.52 of FP32 peak on this workload (DESIGN.md section 4: "
+                   "0.62 useful interactions per evaluated lane-slot x 20/24 flop per FMA-pipe clock)",
         "note": "per GPU; not tensor-core work (no dense contraction); HBM phases under 'phases'",
     }
+    # HBM phases: bytes one rank moves / that rank's time.  With N > 1 the key generation and the radix sort run over the
+    # rank's slice only (sharded sort); gather, build, extract and integrate are replicated over all bodies.
+    shard = m["shard_bodies"]
+    phase_bodies = {"keygen": shard, "sort": shard}
     phases = {}
     for k, v in m["phase"].items():
         e = {"ms": v}
         if k in PHASE_BYTES and v > 0:
-            gbs = PHASE_BYTES[k] * n / (v * 1e-3) / 1e9
-            e.update(algorithmic_bytes_per_body=PHASE_BYTES[k], achieved_gbs=gbs, frac_of_hbm_peak=gbs / peaks["hbm_gbs"])
+            nb = phase_bodies.get(k, n) if world > 1 else n
+            gbs = PHASE_BYTES[k] * nb / (v * 1e-3) / 1e9
+            e.update(algorithmic_bytes_per_body=PHASE_BYTES[k], bodies_this_rank=nb, achieved_gbs=gbs, frac_of_hbm_peak=gbs / peaks["hbm_gbs"])
+            if world > 1 and k == "gather":
+                e["note"] = "includes the key/value all-gathers of the sharded sort and the merge of the sorted runs"
         phases[k] = e
 
     # the largest HBM-bound phase (radix sort) against the measured copy bandwidth
-    sort_bytes = PHASE_BYTES["sort"] * n
+    sort_bodies = shard if world > 1 else n
+    sort_bytes = PHASE_BYTES["sort"] * sort_bodies
     sort_ms = m["phase"].get("sort", 0.0)
     roofline_hbm = None
     if sort_ms > 0:
         gbs = sort_bytes / (sort_ms * 1e-3) / 1e9
         roofline_hbm = {"kernel": "hist_kernel + 8 x onesweep_kernel (radix sort of 63-bit keys + 32-bit payload)", "bound": "hbm",
                         "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                        "traffic": (_traffic(key, "sort") if n == cfg["num_bodies"] else None),
-                        "algorithmic_bytes_per_launch": sort_bytes, "launch_ms": sort_ms, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)"}
+                        "traffic": (_traffic(key, "sort") if n == cfg["num_bodies"] and world == 1 else None),
+                        "algorithmic_bytes_per_launch": sort_bytes, "bodies_this_rank": sort_bodies, "launch_ms": sort_ms,
+                        "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)"}
     line = {
         "metric": "body_updates_per_sec", "value": m["value"], "unit": "body-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": m["ms_per_step"],
@@ -505,6 +695,9 @@ def run_gpu(args):
         "e2e": m.get("e2e"), "gpu_launches": m["launches"], "clocks": m["clocks"],
         "host_generate_s": m["gen_s"],
     }
+    if m.get("replicas") is not None:
+        line["replicas"] = m["replicas"]
+        line["replicas_identical"] = bool(m["replicas"]["replicas_identical"] and m["replicas"]["matches_single_gpu_replay"] is not False)
     if rank == 0 and world == 1:
         line["cpu_baseline"] = cpu_baseline(cfg, m["pos"], m["vel"], m["mass"])
     del m
@@ -514,7 +707,8 @@ def run_gpu(args):
         line["also"] = {"workload": "4k_collision_1m", "bodies": a["n"], "theta": a["cfg"]["theta"],
                         "value": a["value"], "unit": "body-updates/s", "ms_per_step": a["ms_per_step"],
                         "phases_ms": a["phase"], "interactions_per_body": a["inter_step"] / a["n"],
-                        "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                        "roofline": {"kernel": "traverse64_kernel" if a["stats"].get("trav_kernel") == 64 else "traverse_kernel",
+                                     "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                                      "frac": ach / fp32_peak if fp32_peak else None},
                         "e2e": a.get("e2e"),
                         "cpu_baseline": cpu_baseline(a["cfg"], a["pos"], a["vel"], a["mass"])}

@@ -52,6 +52,9 @@ typedef struct b200_nbody_stats {
     int64_t trav_batches;      /* select/load/eval/expand rounds */
     int64_t trav_stack_max;    /* high-water mark of a warp's stack (capacity 512) */
     int64_t trav_shared_pairs; /* pair records evaluated for both 32-body halves of a 64-body tile from one staging */
+    int32_t trav_kernel;       /* walk of the last traversal launch: 32 = traverse_kernel (one body per lane), 64 = traverse64_kernel */
+    int32_t reserved0;
+    int64_t trav_sure_pairs;   /* (pair, half) evaluations the tile-level box test let skip the per-lane MAC (classed walk) */
 } b200_nbody_stats;
 
 const char* b200_last_error(void);
@@ -120,6 +123,12 @@ int b200_nbody_set_profiling(b200_nbody* h, int enabled);
 /* Exact device-side interaction counting in step() (stats.interactions); off by default because
  * it costs a few instructions in the traversal's inner loop.  compute_accelerations always counts. */
 int b200_nbody_set_counting(b200_nbody* h, int enabled);
+/* Exact accepted-interaction count of one force pass over the handle's shard on the CURRENT state (tree
+ * built if needed, nothing integrated, nothing copied out): what bench.py divides the timed traversal by. */
+int b200_nbody_count_interactions(b200_nbody* h, int64_t* interactions);
+/* Order-independent 64-bit checksums of the fp64 master state (positions, velocities), keyed by creation
+ * index: equal on two handles iff they hold bit-identical states.  bench.py compares replicas with it. */
+int b200_nbody_state_checksum(b200_nbody* h, uint64_t out[2]);
 /* Runs nsteps steps and returns their device time (CUDA events on the handle's stream). */
 int b200_nbody_timed_steps(b200_nbody* h, double dt, int nsteps, float* elapsed_ms);
 /* Kernels launched by this handle so far (bench.py's gpu_launches). */

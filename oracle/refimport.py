@@ -1,9 +1,11 @@
-"""Import the UNMODIFIED reference kernels headless (authoring container only).
+"""Import the UNMODIFIED reference kernels headless.
 
-TEST INFRASTRUCTURE ONLY.  /root/reference does not exist on the GPU box, so nothing that
-runs there (-m gpu tests, smoke(), bench.py) may call this; it is used by
-tests/golden/make_golden.py to generate fixtures and by CPU tests that cross-check the
-oracle against the live reference when the tree is present (skipped otherwise).
+TEST INFRASTRUCTURE ONLY.  The reference tree is looked up at B200SIM_REFERENCE_ROOT, then
+/root/reference (authoring container), then oracle/_ref (the git-ignored verbatim copy made by
+oracle/make_ref.py, which travels to the GPU box).  Used by tests/golden/make_golden.py to generate
+fixtures, by tests that cross-check the oracle / the CUDA path against the live reference (skipped when
+no tree is present) and by `bench.py --impl reference` / its `cpu_baseline` leg.  The product package
+never imports this module.
 
 The reference hard-imports PyOpenGL at module top (nbody/simulation.py:16-17,
 boids/flock.py:6-7), which is not installed: empty stub modules are registered first.
@@ -16,7 +18,15 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("B200SIM_REFERENCE_ROOT", "/root/reference")
+def _find_root() -> str:
+    here = os.path.dirname(os.path.abspath(__file__))
+    for cand in (os.environ.get("B200SIM_REFERENCE_ROOT"), "/root/reference", os.path.join(here, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "nbody")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:
@@ -43,29 +53,54 @@ def _stub_opengl() -> None:
 
 def _stub_zstandard() -> None:
     """tools/record.py:228 hard-imports `zstandard` (not installed): a minimal shim over the system
-    libzstd (the same binding the product's codec uses) with the two classes the recorder touches."""
+    libzstd with the two classes the recorder touches.  The binding is this module's own (ctypes on
+    libzstd.so.1), independent of the product's codec, so frames written through it are not circular
+    evidence for the product's codec."""
     if "zstandard" in sys.modules:
         return
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    if root not in sys.path:
-        sys.path.insert(0, root)
-    import b200sim  # noqa: F401
-    from b200sim import codec
+    import ctypes as C
+    import ctypes.util
+    z = C.CDLL(ctypes.util.find_library("zstd") or "libzstd.so.1")
+    z.ZSTD_compressBound.restype = C.c_size_t
+    z.ZSTD_compressBound.argtypes = [C.c_size_t]
+    z.ZSTD_compress.restype = C.c_size_t
+    z.ZSTD_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]
+    z.ZSTD_decompress.restype = C.c_size_t
+    z.ZSTD_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    z.ZSTD_getFrameContentSize.restype = C.c_ulonglong
+    z.ZSTD_getFrameContentSize.argtypes = [C.c_char_p, C.c_size_t]
+    z.ZSTD_isError.restype = C.c_uint
+    z.ZSTD_isError.argtypes = [C.c_size_t]
+    z.ZSTD_versionString.restype = C.c_char_p
 
     class ZstdCompressor:
         def __init__(self, level=3, threads=0, **_kw):
             self.level = level
 
         def compress(self, data):
-            return codec.zstd_compress(bytes(data), self.level, 0)
+            data = bytes(data)
+            cap = z.ZSTD_compressBound(len(data))
+            buf = C.create_string_buffer(cap)
+            n = z.ZSTD_compress(buf, cap, data, len(data), self.level)
+            if z.ZSTD_isError(n):
+                raise RuntimeError("ZSTD_compress failed")
+            return buf.raw[:n]
 
     class ZstdDecompressor:
         def decompress(self, data, max_output_size=0):
-            return codec.zstd_decompress(bytes(data))
+            data = bytes(data)
+            size = z.ZSTD_getFrameContentSize(data, len(data))
+            if size >= (1 << 62):
+                size = max_output_size or 64 * len(data)
+            buf = C.create_string_buffer(int(size) or 1)
+            n = z.ZSTD_decompress(buf, int(size), data, len(data))
+            if z.ZSTD_isError(n):
+                raise RuntimeError("ZSTD_decompress failed")
+            return buf.raw[:n]
 
     m = types.ModuleType("zstandard")
     m.ZstdCompressor, m.ZstdDecompressor = ZstdCompressor, ZstdDecompressor
-    m.__version__ = "shim-libzstd-" + codec.zstd_version()
+    m.__version__ = "shim-libzstd-" + z.ZSTD_versionString().decode()
     sys.modules["zstandard"] = m
 
 

@@ -18,7 +18,7 @@ __device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.app
 
 struct Body { float npx, npy, npz; float2 ax, ay, az; };
 
-template <int MODE>   // 0: MAC  1: masked, no MAC  2: plain
+template <int MODE>   // 0: MAC  1: masked (predicated MUFU), no MAC  2: plain  3: masked by predicated accumulation, no MAC
 __device__ __forceinline__ void eval(const float4& XY, const float4& ZM, float T0, float T1, unsigned mask, unsigned lanebit, float2 eps22,
                                      Body& b, unsigned& om0, unsigned& om1)
 {
@@ -43,9 +43,17 @@ __device__ __forceinline__ void eval(const float4& XY, const float4& ZM, float T
         r.y = rsqrt_approx(d2.y);
     }
     const float2 f = __fmul2_rn(make_float2(ZM.z, ZM.w), __fmul2_rn(__fmul2_rn(r, r), r));
-    b.ax = __ffma2_rn(dx, f, b.ax);
-    b.ay = __ffma2_rn(dy, f, b.ay);
-    b.az = __ffma2_rn(dz, f, b.az);
+    if (MODE == 3) {
+        if ((mask & lanebit) != 0u) {
+            b.ax = __ffma2_rn(dx, f, b.ax);
+            b.ay = __ffma2_rn(dy, f, b.ay);
+            b.az = __ffma2_rn(dz, f, b.az);
+        }
+    } else {
+        b.ax = __ffma2_rn(dx, f, b.ax);
+        b.ay = __ffma2_rn(dy, f, b.ay);
+        b.az = __ffma2_rn(dz, f, b.az);
+    }
 }
 
 template <int MODE, int NB, int MINB>
@@ -72,7 +80,9 @@ __global__ void __launch_bounds__(256, MINB) evalk(float4* out, int iters, int P
     for (int it = 0; it < iters; ++it) {
 #pragma unroll 2
         for (int j = 0; j < P; ++j) {
-            const float4 XY = sXY[j], ZM = sZM[j], TM = sTM[j];
+            const float4 XY = sXY[j], ZM = sZM[j];
+            float4 TM = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODE != 2) TM = sTM[j];
             unsigned om[2 * NB];
 #pragma unroll
             for (int q = 0; q < NB; ++q) {
@@ -169,6 +179,9 @@ int main()
             run<2, 1, 3>("no MAC, full mask, 1 body/lane", d, c);
             run<0, 4, 3>("MAC, 4 bodies/lane", d, c);
             run<2, 4, 3>("no MAC, full mask, 4 bodies/lane", d, c);
+            run<3, 2, 3>("no MAC, predicated accumulate, 2 bodies/lane", d, c);
+            run<3, 1, 3>("no MAC, predicated accumulate, 1 body/lane", d, c);
+            run<1, 1, 3>("no MAC, masked (MUFU pred), 1 body/lane", d, c);
         } else {
             run<0, 2, 4>("MAC, 2 bodies/lane (shipped both-loop)", d, c);
             run<1, 2, 4>("no MAC, masked, 2 bodies/lane", d, c);

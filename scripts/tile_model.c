@@ -68,7 +68,7 @@ void tile_model(const double* pos, const double* half, const double* com, const 
             }
             cx = 0.5 * (lo[0] + hi[0]); cy = 0.5 * (lo[1] + hi[1]); cz = 0.5 * (lo[2] + hi[2]);
             /* per-half bounding spheres (64-body tiles) */
-            double hc[2][3] = {{0, 0, 0}, {0, 0, 0}}, hR[2] = {0, 0};
+            double hc[2][3] = {{0, 0, 0}, {0, 0, 0}}, hR[2] = {0, 0}, hlo[2][3] = {{0}}, hhi[2][3] = {{0}};
             for (int h = 0; h < 2; ++h) {
                 double l2[3] = {1e300, 1e300, 1e300}, h2[3] = {-1e300, -1e300, -1e300};
                 const int a = 32 * h, b = nb < 32 * (h + 1) ? (int)nb : 32 * (h + 1);
@@ -78,7 +78,7 @@ void tile_model(const double* pos, const double* half, const double* com, const 
                     if (py[l] < l2[1]) l2[1] = py[l]; if (py[l] > h2[1]) h2[1] = py[l];
                     if (pz[l] < l2[2]) l2[2] = pz[l]; if (pz[l] > h2[2]) h2[2] = pz[l];
                 }
-                for (int d = 0; d < 3; ++d) hc[h][d] = 0.5 * (l2[d] + h2[d]);
+                for (int d = 0; d < 3; ++d) { hc[h][d] = 0.5 * (l2[d] + h2[d]); hlo[h][d] = l2[d]; hhi[h][d] = h2[d]; }
                 for (int l = a; l < b; ++l) {
                     const double d = sqrt((px[l] - hc[h][0]) * (px[l] - hc[h][0]) + (py[l] - hc[h][1]) * (py[l] - hc[h][1]) + (pz[l] - hc[h][2]) * (pz[l] - hc[h][2]));
                     if (d > hR[h]) hR[h] = d;
@@ -153,6 +153,15 @@ void tile_model(const double* pos, const double* half, const double* com, const 
                         const double dh = sqrt((com[3 * c] - hc[h][0]) * (com[3 * c] - hc[h][0]) + (com[3 * c + 1] - hc[h][1]) * (com[3 * c + 1] - hc[h][1]) +
                                                (com[3 * c + 2] - hc[h][2]) * (com[3 * c + 2] - hc[h][2]));
                         sure_h[h][k] = leaf[k] || S < 0 || (dh - hR[h] > S * 1.00001);
+                        if (getenv("TILE_AABB")) {   /* axis-aligned box of the half instead of its sphere */
+                            double m2 = 0;
+                            for (int d = 0; d < 3; ++d) {
+                                const double cc = com[3 * c + d];
+                                const double q = cc < hlo[h][d] ? hlo[h][d] - cc : (cc > hhi[h][d] ? cc - hhi[h][d] : 0.0);
+                                m2 += q * q;
+                            }
+                            sure_h[h][k] = leaf[k] || S < 0 || (m2 > S * S * 1.00002);
+                        }
                     }
                     if (om) {
                         if (sp + 1 >= cap) { cap *= 2; snode = (int32_t*)realloc(snode, sizeof(int32_t) * cap); smask = (uint64_t*)realloc(smask, sizeof(uint64_t) * cap); }

@@ -26,7 +26,7 @@ def test_struct_sizes_match_header_layout():
     from b200sim import _lib
     import ctypes as C
     assert C.sizeof(_lib.BoidsParams) == 11 * 8
-    assert C.sizeof(_lib.NBodyStats) == 8 * 5 + 4 + 4 + 8 + 8 + 8 * 8 + 8 + 5 * 8
+    assert C.sizeof(_lib.NBodyStats) == 8 * 5 + 4 + 4 + 8 + 8 + 8 * 8 + 8 + 5 * 8 + 4 + 4 + 8
     assert C.sizeof(_lib.BoidsStats) == 8 * 3 + 4 + 4 + 8 * 2 + 8 * 4 + 8 * 5
 
 

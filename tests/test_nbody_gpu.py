@@ -191,9 +191,10 @@ def test_coincident_bodies_and_degenerate_layouts():
     assert _rms_rel(acc, ref) <= ACC_RMS_TOL
 
 
-@pytest.mark.parametrize("walk", ["32", "64"])
+@pytest.mark.parametrize("walk", ["32", "64", "64o"])
 def test_every_walk_variant_makes_the_reference_mac_decisions(walk, monkeypatch):
-    """The traversal kernels (one body per lane, two bodies per lane) are forced in
+    """The traversal kernels (one body per lane; two bodies per lane with the tile-level box classes; the
+    unclassed two-body walk) are forced in
     turn (the default picks per launch): same interaction lists as the oracle -- accelerations within
     the stated tolerance, interaction counts equal -- on a clustered case, a bucket of coincident
     bodies (multi-pair stack entries) and ragged tile ends."""
