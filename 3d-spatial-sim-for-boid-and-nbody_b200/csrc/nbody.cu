@@ -89,8 +89,10 @@ __global__ void __launch_bounds__(256) keygen_kernel(const double* __restrict__ 
 }
 
 // ============================================================================ gather
-// Physically reorder the master state into the new Morton order (nearly the identity after
-// the first step, so the reads stay close to coalesced) and emit the float4 view.
+// Physically reorder positions, masses and ids into the new Morton order (nearly the identity after
+// the first step, so the reads stay close to coalesced) and emit the float4 view.  Inside step() the
+// velocities are NOT moved here: the traversal's epilogue fetches them through the permutation when it
+// integrates (vel_in == nullptr); the other callers (getters, the split multi-GPU step) reorder them too.
 struct GatherArgs {
     const uint32_t* __restrict__ perm;
     const double* __restrict__ pos_in; const double* __restrict__ vel_in; const double* __restrict__ mass_in;
@@ -112,11 +114,13 @@ __device__ __forceinline__ void gather_block(int block, const GatherArgs& a, int
     if (k >= n) return;
     const int64_t j = perm[k];
     const double x = pos_in[3 * j], y = pos_in[3 * j + 1], z = pos_in[3 * j + 2];
-    const double vx = vel_in[3 * j], vy = vel_in[3 * j + 1], vz = vel_in[3 * j + 2];
     const double m = mass_in[j];
     const int64_t o = 3 * (int64_t)k;
     pos_out[o] = x; pos_out[o + 1] = y; pos_out[o + 2] = z;
-    vel_out[o] = vx; vel_out[o + 1] = vy; vel_out[o + 2] = vz;
+    if (vel_in) {
+        const double vx = vel_in[3 * j], vy = vel_in[3 * j + 1], vz = vel_in[3 * j + 2];
+        vel_out[o] = vx; vel_out[o + 1] = vy; vel_out[o + 2] = vz;
+    }
     mass_out[k] = m;
     id_out[k] = id_in[j];
     posm[k] = make_float4((float)x, (float)y, (float)z, (float)m);
@@ -668,8 +672,8 @@ void nbody_alloc(NBodySim& s, int n)
     B200_CHECK(cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking));
     s.stream = s.own_stream;
     const size_t N = (size_t)n;
+    for (int b = 0; b < 3; ++b) s.pos[b] = alloc_counted<double>(s, 3 * N);
     for (int b = 0; b < 2; ++b) {
-        s.pos[b] = alloc_counted<double>(s, 3 * N);
         s.vel[b] = alloc_counted<double>(s, 3 * N);
         s.mass[b] = alloc_counted<double>(s, N);
         s.id[b] = alloc_counted<uint32_t>(s, N);
@@ -713,8 +717,10 @@ void nbody_alloc(NBodySim& s, int n)
     B200_CHECK(cudaHostAlloc(&s.h_error, sizeof(unsigned), cudaHostAllocDefault));
     *s.h_error = 0;
     B200_CHECK(cudaMemset(s.d_interactions, 0, TRAV_COUNTERS * sizeof(unsigned long long)));
-    B200_CHECK(cudaFuncSetAttribute(traverse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV_SMEM_BYTES));
-    B200_CHECK(cudaFuncSetAttribute(traverse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV_SMEM_BYTES));
+    B200_CHECK(cudaFuncSetAttribute(traverse_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV_SMEM_BYTES));
+    B200_CHECK(cudaFuncSetAttribute(traverse_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV_SMEM_BYTES));
+    B200_CHECK(cudaFuncSetAttribute(traverse_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV_SMEM_BYTES));
+    B200_CHECK(cudaFuncSetAttribute(traverse_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV_SMEM_BYTES));
     {
         // B200_TRAV = 32 | 64 forces a walk; default: chosen per launch (see nbody_traverse)
         // (tests shrink these to exercise the bucketed un-permute at small n)
@@ -724,12 +730,12 @@ void nbody_alloc(NBodySim& s, int n)
         const char* ng = getenv("B200_NO_GRAPH");   // plain launches instead of the captured step (debugging, A/B timing)
         s.use_graph = !(ng && ng[0] == '1');
         const char* mode = getenv("B200_TRAV");
-        s.trav_mode = !mode ? 0 : (mode[0] == '6' ? (mode[1] == '4' && mode[2] == 'o' ? 63 : 64) : 32);   // "64o": the unclassed 64-body walk
+        s.trav_mode = !mode ? 0 : (mode[0] == '6' ? 64 : 32);
     }
-    B200_CHECK(cudaFuncSetAttribute(traverse64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV64_SMEM_BYTES));
-    B200_CHECK(cudaFuncSetAttribute(traverse64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV64_SMEM_BYTES));
-    B200_CHECK(cudaFuncSetAttribute(traverse64c_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV64C_SMEM_BYTES));
-    B200_CHECK(cudaFuncSetAttribute(traverse64c_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV64C_SMEM_BYTES));
+    B200_CHECK(cudaFuncSetAttribute(traverse64c_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV64C_SMEM_BYTES));
+    B200_CHECK(cudaFuncSetAttribute(traverse64c_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV64C_SMEM_BYTES));
+    B200_CHECK(cudaFuncSetAttribute(traverse64c_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV64C_SMEM_BYTES));
+    B200_CHECK(cudaFuncSetAttribute(traverse64c_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAV64C_SMEM_BYTES));
     B200_CHECK(cudaMemset(s.colors, 0, 3 * N * sizeof(float)));
     s.shard_begin = 0;
     s.shard_end = n;
@@ -744,9 +750,10 @@ void nbody_free(NBodySim& s)
     if (s.stream) cudaStreamSynchronize(s.stream);
     nbody_graphs_reset(s);
     for (int b = 0; b < 2; ++b) {
-        cudaFree(s.pos[b]); cudaFree(s.vel[b]); cudaFree(s.mass[b]); cudaFree(s.id[b]);
+        cudaFree(s.vel[b]); cudaFree(s.mass[b]); cudaFree(s.id[b]);
         cudaFree(s.keys[b]); cudaFree(s.vals[b]);
     }
+    for (int b = 0; b < 3; ++b) cudaFree(s.pos[b]);
     cudaFree(s.mass0);
     s.sorter.destroy();
     if (s.ms_keys) { cudaFree(s.ms_keys); cudaFree(s.ms_vals); s.ms_keys = nullptr; s.ms_vals = nullptr; }
@@ -773,7 +780,7 @@ static void recompute_maxabs(NBodySim& s)
         const int64_t count = 3 * (int64_t)s.n;
         const int64_t want = (count + 255) / 256, cap = (int64_t)s.sm_count * 16;
         const int blocks = (int)(want < cap ? want : cap);
-        absmax_kernel<<<blocks, 256, 0, s.stream>>>(s.pos[s.cur], count, s.d_maxabs);
+        absmax_kernel<<<blocks, 256, 0, s.stream>>>(s.pos[s.pcur], count, s.d_maxabs);
         ++s.launches;
         B200_CHECK(cudaGetLastError());
     }
@@ -783,7 +790,8 @@ void nbody_upload(NBodySim& s, const double* pos, const double* vel, const doubl
 {
     B200_CHECK(cudaSetDevice(s.device));
     const size_t N = (size_t)s.n;
-    s.cur = 0;
+    s.pcur = 0;
+    s.vcur = 0;
     B200_CHECK(cudaMemcpyAsync(s.pos[0], pos, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     B200_CHECK(cudaMemcpyAsync(s.vel[0], vel, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     B200_CHECK(cudaMemcpyAsync(s.mass[0], mass, N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
@@ -801,23 +809,27 @@ void nbody_upload_state(NBodySim& s, const double* pos, const double* vel)
     const size_t N = (size_t)s.n;
     // bring masses back to creation order alongside: simplest is to scatter through id[]
     // into the other buffer, then continue from there with id = iota.
-    const int o = s.cur ^ 1;
-    B200_CHECK(cudaMemcpyAsync(s.pos[o], pos, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    const int po = (s.pcur + 1) % 3, o = s.vcur ^ 1;
+    B200_CHECK(cudaMemcpyAsync(s.pos[po], pos, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     B200_CHECK(cudaMemcpyAsync(s.vel[o], vel, 3 * N * sizeof(double), cudaMemcpyHostToDevice, s.stream));
     if (s.n > 0) {
         // masses back in creation order: a copy of the kept array (a scatter through id[] costs 2 ms at 50 M)
         B200_CHECK(cudaMemcpyAsync(s.mass[o], s.mass0, (size_t)s.n * sizeof(double), cudaMemcpyDeviceToDevice, s.stream));
         iota_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.id[o], s.n);
     }
-    s.cur = o;
+    s.pcur = po;
+    s.vcur = o;
     recompute_maxabs(s);
     s.tree_valid = false;
     B200_CHECK(cudaStreamSynchronize(s.stream));
 }
 
-static void build_after_sort(NBodySim& s);
+static void build_after_sort(NBodySim& s, bool for_step);
+static void build_tree_impl(NBodySim& s, bool for_step);
 
-void nbody_build_tree(NBodySim& s)
+void nbody_build_tree(NBodySim& s) { build_tree_impl(s, false); }
+
+static void build_tree_impl(NBodySim& s, bool for_step)
 {
     B200_CHECK(cudaSetDevice(s.device));
     const int n = s.n;
@@ -826,7 +838,7 @@ void nbody_build_tree(NBodySim& s)
     cudaStream_t st = s.stream;
     s.timer.begin(st);
     // ---- keys
-    keygen_kernel<<<grid, 256, 0, st>>>(s.pos[s.cur], 0, n, s.d_maxabs + s.maxabs_slot, s.keys[0], s.d_bounds, s.d_ttab, s.theta,
+    keygen_kernel<<<grid, 256, 0, st>>>(s.pos[s.pcur], 0, n, s.d_maxabs + s.maxabs_slot, s.keys[0], s.d_bounds, s.d_ttab, s.theta,
                                         (float)(s.softening * s.softening));
     ++s.launches;
     B200_CHECK(cudaGetLastError());
@@ -835,7 +847,7 @@ void nbody_build_tree(NBodySim& s)
     s.sorted_slot = s.sorter.sort(s.keys, s.vals, 0, n, 0, 64, /*iota=*/true, st, s.sm_count);
     s.launches += s.sorter.last_launches;
     s.timer.mark(st);
-    build_after_sort(s);
+    build_after_sort(s, for_step);
 }
 
 // ---------------------------------------------------------------------------- sharded sort (multi-GPU)
@@ -934,7 +946,7 @@ void nbody_ms_sort_local(NBodySim& s, int rank)
     uint32_t* v2[2] = {s.ms_vals + (size_t)rank * s.ms_slice, s.vals[1] + begin};
     // (rank 0's launch also writes bounds and the threshold table; every rank runs with len >= 0, and
     // a rank with an empty slice still needs them)
-    keygen_kernel<<<max(1, div_up(len, 256)), 256, 0, st>>>(s.pos[s.cur], begin, begin + len, s.d_maxabs + s.maxabs_slot, k2[0],
+    keygen_kernel<<<max(1, div_up(len, 256)), 256, 0, st>>>(s.pos[s.pcur], begin, begin + len, s.d_maxabs + s.maxabs_slot, k2[0],
                                                              s.d_bounds, s.d_ttab, s.theta, (float)(s.softening * s.softening));
     ++s.launches;
     B200_CHECK(cudaGetLastError());
@@ -960,7 +972,7 @@ void nbody_build_tree_presorted(NBodySim& s)
     ++s.launches;
     B200_CHECK(cudaGetLastError());
     s.sorted_slot = 0;
-    build_after_sort(s);
+    build_after_sort(s, false);
 }
 
 __global__ void init_build_counters_kernel(unsigned* alloc, unsigned* children)
@@ -969,22 +981,31 @@ __global__ void init_build_counters_kernel(unsigned* alloc, unsigned* children)
     *children = 0u;
 }
 
-static void build_after_sort(NBodySim& s)
+// for_step: called by step(): the velocities stay where they are (the fused traversal + integration reads them
+// through the permutation) and the state buffers are only advanced once that kernel has been launched.
+static void build_after_sort(NBodySim& s, bool for_step)
 {
     const int n = s.n;
     const int grid = div_up(n, 256);
     cudaStream_t st = s.stream;
     // ---- physical reorder
-    const int o = s.cur ^ 1;
+    const int gp = (s.pcur + 1) % 3, o = s.vcur ^ 1;
     {
-        const GatherArgs ga{s.vals[s.sorted_slot], s.pos[s.cur], s.vel[s.cur], s.mass[s.cur], s.id[s.cur],
-                            s.pos[o], s.vel[o], s.mass[o], s.id[o], s.posm};
+        const GatherArgs ga{s.vals[s.sorted_slot], s.pos[s.pcur], for_step ? nullptr : s.vel[s.vcur], s.mass[s.vcur], s.id[s.vcur],
+                            s.pos[gp], s.vel[o], s.mass[o], s.id[o], s.posm};
         const KarrasArgs ka{s.keys[s.sorted_slot], s.childL, s.childR, s.parent, s.range, s.lvl};
         gather_karras_kernel<<<2 * grid, 256, 0, st>>>(ga, ka, n);   // phase "gather" = reorder + tree topology
     }
     ++s.launches;
     B200_CHECK(cudaGetLastError());
-    s.cur = o;
+    const double* pos_sorted = s.pos[gp];
+    const double* mass_sorted = s.mass[o];
+    if (for_step) {
+        s.step_pending = true;     // pos[gp], mass[o], id[o] hold the new order; vel[vcur] still the previous one
+    } else {
+        s.pcur = gp;               // the whole state is in the new order
+        s.vcur = o;
+    }
     s.timer.mark(st);
     // ---- blocked prefix sums of (m x, m y, m z, m) = node mass / centre of mass; pass 1 of the cell
     // extraction (children lists, pair-block allocation)
@@ -994,7 +1015,7 @@ static void build_after_sort(NBodySim& s)
         const ChildrenArgs ca{s.childL, s.childR, s.parent, s.range, s.lvl, s.meta, s.ishead, s.kids,
                               s.d_alloc, (unsigned)(s.rec_capacity_override > 0 ? min(s.rec_capacity, s.rec_capacity_override) : s.rec_capacity),
                               s.d_error, s.d_children};
-        prefix_kernel<<<nb, 256, 0, st>>>(s.pos[s.cur], s.mass[s.cur], n, s.ploc, s.bex);
+        prefix_kernel<<<nb, 256, 0, st>>>(pos_sorted, mass_sorted, n, s.ploc, s.bex);
         prefix_blocks_kernel<<<1, 1024, 0, st>>>(s.bex, nb);
         count_children_kernel<<<div_up(n - 1, 256), 256, 0, st>>>(n, ca);
         s.launches += 3;
@@ -1017,62 +1038,55 @@ static void build_after_sort(NBodySim& s)
     s.tree_valid = true;
 }
 
-void nbody_traverse(NBodySim& s, int begin, int end)
+// Launches the walk over sorted bodies [begin, end).  so == nullptr: forces only (s.acc); otherwise the kernel's
+// epilogue also integrates the bodies it traversed and writes the next state (see StepOut in traverse.cuh).
+template <bool COUNT, bool INTEG>
+static void traverse_launch_t(NBodySim& s, int mode, int begin, int end, const StepOut& so)
+{
+    cudaStream_t st = s.stream;
+    const float eps2 = (float)(s.softening * s.softening);
+    const int stop = min(end, s.n);
+    if (mode == 64) {
+        const int tiles64 = div_up(stop - begin, 64);
+        const int blocks = min(div_up(tiles64, TRAV_WARPS), s.sm_count * 3);
+        traverse64c_kernel<COUNT, INTEG><<<blocks, TRAV_BLOCK, TRAV64C_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, begin, stop, eps2, (float)s.G,
+                                                                                        s.d_tile_counter, s.d_interactions, s.d_error, so);
+    } else {
+        const int tile_begin = begin / 32, tile_end = div_up(end, 32);
+        const int blocks = min(div_up(tile_end - tile_begin, TRAV_WARPS), s.sm_count * 4);
+        traverse_kernel<COUNT, INTEG><<<blocks, TRAV_BLOCK, TRAV_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, tile_begin, tile_end, stop, eps2, (float)s.G,
+                                                                                  s.d_tile_counter, s.d_interactions, s.d_error, so);
+    }
+}
+
+static void traverse_launch(NBodySim& s, int begin, int end, const StepOut* so)
 {
     B200_CHECK(cudaSetDevice(s.device));
     cudaStream_t st = s.stream;
     if (end > begin) {
         B200_REQUIRE(begin % 32 == 0, "traversal range must start on a 32-body tile");
-        const int tile_begin = begin / 32, tile_end = div_up(end, 32);
         B200_CHECK(cudaMemsetAsync(s.d_tile_counter, 0, sizeof(unsigned), st));
-        const int tiles = tile_end - tile_begin;
-        const float eps2 = (float)(s.softening * s.softening);
-        // Two bodies per lane pay off when neighbouring 32-body tiles share most of their interaction
-        // lists (large N, large theta: 0.90 of the pair evaluations are shared at 50 M / theta 0.7, 0.80 at
-        // 1 M / theta 0.5); measured on B200: -5 % at 50 M / 0.7, +5 % at 1 M / 0.5, break-even near 4 M / 0.7.
-        const int mode = s.trav_mode ? s.trav_mode : (s.theta >= 0.65 && s.n >= 8000000 ? 64 : 32);
-        s.last_trav_kernel = mode == 63 ? 64 : mode;
-        if (mode == 64) {
-            const int tiles64 = div_up(min(end, s.n) - begin, 64);
-            const int blocks = min(div_up(tiles64, TRAV_WARPS), s.sm_count * 3);
-            if (s.count_interactions)
-                traverse64c_kernel<true><<<blocks, TRAV_BLOCK, TRAV64C_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, begin, min(end, s.n), eps2, (float)s.G,
-                                                                                        s.d_tile_counter, s.d_interactions, s.d_error);
-            else
-                traverse64c_kernel<false><<<blocks, TRAV_BLOCK, TRAV64C_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, begin, min(end, s.n), eps2, (float)s.G,
-                                                                                         s.d_tile_counter, s.d_interactions, s.d_error);
-            ++s.launches;
-            B200_CHECK(cudaGetLastError());
-            s.timer.mark(st);
-            return;
+        // Two bodies per lane (64-body tiles, the classed walk) win from about a million bodies up: measured on
+        // B200 4.79 vs 5.23 ms at 8 M / theta 0.7, 26.0 vs 30.6 at 50 M, a tie at 1 M / theta 0.5; below that the
+        // 32-body tiles give the machine twice as many warps to schedule.
+        const int mode = s.trav_mode ? s.trav_mode : (s.n >= 1000000 ? 64 : 32);
+        B200_REQUIRE(mode == 32 || begin % 64 == 0, "the 64-body walk needs a range that starts on a 64-body tile");
+        s.last_trav_kernel = mode;
+        const StepOut none{};
+        if (so) {
+            if (s.count_interactions) traverse_launch_t<true, true>(s, mode, begin, end, *so);
+            else traverse_launch_t<false, true>(s, mode, begin, end, *so);
+        } else {
+            if (s.count_interactions) traverse_launch_t<true, false>(s, mode, begin, end, none);
+            else traverse_launch_t<false, false>(s, mode, begin, end, none);
         }
-        if (mode == 63) {
-            const int tiles64 = div_up(min(end, s.n) - begin, 64);
-            const int blocks = min(div_up(tiles64, TRAV_WARPS), s.sm_count * 3);
-            if (s.count_interactions)
-                traverse64_kernel<true><<<blocks, TRAV_BLOCK, TRAV64_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, begin, min(end, s.n), eps2, (float)s.G,
-                                                                                      s.d_tile_counter, s.d_interactions, s.d_error);
-            else
-                traverse64_kernel<false><<<blocks, TRAV_BLOCK, TRAV64_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, begin, min(end, s.n), eps2, (float)s.G,
-                                                                                       s.d_tile_counter, s.d_interactions, s.d_error);
-            ++s.launches;
-            B200_CHECK(cudaGetLastError());
-            s.timer.mark(st);
-            return;
-        }
-        const int max_blocks = s.sm_count * 4;
-        const int blocks = min(div_up(tiles, TRAV_WARPS), max_blocks);
-        if (s.count_interactions)
-            traverse_kernel<true><<<blocks, TRAV_BLOCK, TRAV_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, tile_begin, tile_end, min(end, s.n),
-                                                                 eps2, (float)s.G, s.d_tile_counter, s.d_interactions, s.d_error);
-        else
-            traverse_kernel<false><<<blocks, TRAV_BLOCK, TRAV_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, tile_begin, tile_end, min(end, s.n),
-                                                                  eps2, (float)s.G, s.d_tile_counter, s.d_interactions, s.d_error);
         ++s.launches;
         B200_CHECK(cudaGetLastError());
     }
     s.timer.mark(st);
 }
+
+void nbody_traverse(NBodySim& s, int begin, int end) { traverse_launch(s, begin, end, nullptr); }
 
 void nbody_integrate(NBodySim& s, double dt)
 {
@@ -1081,7 +1095,7 @@ void nbody_integrate(NBodySim& s, double dt)
     if (s.n > 0) {
         const int next = s.maxabs_slot ^ 1;
         B200_CHECK(cudaMemsetAsync(s.d_maxabs + next, 0, sizeof(unsigned long long), st));
-        integrate_kernel<<<div_up(s.n, 256), 256, 0, st>>>(s.pos[s.cur], s.vel[s.cur], s.acc, s.n, dt, s.damping,
+        integrate_kernel<<<div_up(s.n, 256), 256, 0, st>>>(s.pos[s.pcur], s.vel[s.vcur], s.acc, s.n, dt, s.damping,
                                                            s.d_maxabs + next);
         ++s.launches;
         B200_CHECK(cudaGetLastError());
@@ -1114,6 +1128,52 @@ void nbody_step_end(NBodySim& s, double dt)
     }
 }
 
+// One whole step with the integration fused into the traversal (single GPU): keys -> sort -> gather of
+// positions / masses / ids -> tree -> records -> traversal whose epilogue integrates each tile's bodies and
+// writes the next state.  Phases "exchange" and "integrate" are empty (kept so the phase table keeps its shape).
+static void step_fused(NBodySim& s, double dt)
+{
+    if (s.n == 0) { ++s.steps; return; }
+    build_tree_impl(s, true);
+    cudaStream_t st = s.stream;
+    const int gp = (s.pcur + 1) % 3, np = (s.pcur + 2) % 3, o = s.vcur ^ 1;
+    const int next = s.maxabs_slot ^ 1;
+    B200_CHECK(cudaMemsetAsync(s.d_maxabs + next, 0, sizeof(unsigned long long), st));
+    StepOut so{};
+    so.perm = s.vals[s.sorted_slot];
+    so.vel_prev = s.vel[s.vcur];
+    so.pos_new = s.pos[gp];
+    so.pos_out[0] = s.pos[np];
+    so.vel_out[0] = s.vel[o];
+    so.world = 1;
+    so.dt = dt;
+    so.damping = s.damping;
+    so.maxabs = s.d_maxabs + next;
+    traverse_launch(s, 0, s.n, &so);
+    s.timer.mark(st);   // exchange: nothing
+    s.timer.mark(st);   // integrate: fused into the traversal
+    s.pcur = np;
+    s.vcur = o;
+    s.maxabs_slot = next;
+    s.step_pending = false;
+    s.tree_valid = false;
+    ++s.steps;
+    if (s.timer.enabled) {
+        B200_CHECK(cudaStreamSynchronize(st));
+        s.timer.collect();
+    }
+}
+
+static void step_plain(NBodySim& s, double dt)
+{
+    if (s.shard_begin == 0 && s.shard_end == s.n) {
+        step_fused(s, dt);
+    } else {   // a shard is set (split multi-GPU step driven from outside): forces of the shard, then integrate all
+        nbody_step_begin(s);
+        nbody_step_end(s, dt);
+    }
+}
+
 // ---------------------------------------------------------------------------- captured step
 // A step is ~25 launches and memsets; below a few hundred thousand bodies it is launch-bound (the
 // reference's own CPU-runnable presets: 10 K - 100 K bodies).  On the handle's own stream the whole step
@@ -1121,7 +1181,7 @@ void nbody_step_end(NBodySim& s, double dt)
 // buffers is current and on the parameters, so graphs are cached by that key (the buffers alternate:
 // two graphs in steady state); any change (dt, theta, a new state, a shard) captures a new one.
 struct StepGraphKey {
-    int cur, maxabs_slot, shard_begin, shard_end, trav_mode;
+    int pcur, vcur, maxabs_slot, shard_begin, shard_end, trav_mode;
     double dt, G, softening, damping, theta;
     cudaStream_t stream;
 };
@@ -1130,7 +1190,7 @@ static StepGraphKey step_graph_key(const NBodySim& s, double dt)
 {
     StepGraphKey k;
     memset(&k, 0, sizeof(k));
-    k.cur = s.cur; k.maxabs_slot = s.maxabs_slot; k.shard_begin = s.shard_begin; k.shard_end = s.shard_end;
+    k.pcur = s.pcur; k.vcur = s.vcur; k.maxabs_slot = s.maxabs_slot; k.shard_begin = s.shard_begin; k.shard_end = s.shard_end;
     k.trav_mode = s.trav_mode;
     k.dt = dt; k.G = s.G; k.softening = s.softening; k.damping = s.damping; k.theta = s.theta;
     k.stream = s.stream;
@@ -1151,8 +1211,7 @@ void nbody_step(NBodySim& s, double dt)
     const bool capturable = s.stream != nullptr && s.stream != cudaStreamLegacy && s.stream != cudaStreamPerThread;
     const bool plain = s.timer.enabled || s.count_interactions || !capturable || !s.use_graph || s.n < 2;
     if (plain) {
-        nbody_step_begin(s);
-        nbody_step_end(s, dt);
+        step_plain(s, dt);
         return;
     }
     B200_CHECK(cudaSetDevice(s.device));
@@ -1161,7 +1220,7 @@ void nbody_step(NBodySim& s, double dt)
     int slot = -1;
     for (int i = 0; i < NBodySim::MAX_STEP_GRAPHS; ++i)
         if (s.step_graph[i] && memcmp(s.step_graph_key[i], &key, sizeof(key)) == 0) slot = i;
-    const int cur0 = s.cur, mslot0 = s.maxabs_slot;
+    const int pcur0 = s.pcur, vcur0 = s.vcur, mslot0 = s.maxabs_slot;
     if (slot < 0) {
         slot = (int)(s.step_graph_next++ % NBodySim::MAX_STEP_GRAPHS);
         if (s.step_graph[slot]) { cudaGraphExecDestroy(s.step_graph[slot]); s.step_graph[slot] = nullptr; }
@@ -1169,28 +1228,31 @@ void nbody_step(NBodySim& s, double dt)
         cudaGraph_t g = nullptr;
         B200_CHECK(cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
         try {
-            nbody_step_begin(s);
-            nbody_step_end(s, dt);
+            step_plain(s, dt);
         } catch (...) {
             cudaStreamEndCapture(s.stream, &g);
             if (g) cudaGraphDestroy(g);
-            s.cur = cur0; s.maxabs_slot = mslot0; s.launches = launches0; s.steps = steps0;
+            s.pcur = pcur0; s.vcur = vcur0; s.maxabs_slot = mslot0; s.launches = launches0; s.steps = steps0;
+            s.step_pending = false;
             throw;
         }
         B200_CHECK(cudaStreamEndCapture(s.stream, &g));
         const cudaError_t e = cudaGraphInstantiate(&s.step_graph[slot], g, 0);
         cudaGraphDestroy(g);
-        if (e != cudaSuccess) { s.step_graph[slot] = nullptr; s.cur = cur0; s.maxabs_slot = mslot0; }
+        if (e != cudaSuccess) { s.step_graph[slot] = nullptr; s.pcur = pcur0; s.vcur = vcur0; s.maxabs_slot = mslot0; }
         B200_CHECK(e);
         memcpy(s.step_graph_key[slot], &key, sizeof(key));
         s.step_graph_launches[slot] = s.launches - launches0;
         s.step_graph_sorted_slot[slot] = s.sorted_slot;
+        s.step_graph_pcur[slot] = s.pcur;
+        s.step_graph_vcur[slot] = s.vcur;
         // the capture ran the host side of the step (buffer flips, counters); undo the counters, keep the flips
         s.launches = launches0;
         s.steps = steps0;
     } else {
         // replay: the host-side effects of the step
-        s.cur = cur0 ^ 1;
+        s.pcur = s.step_graph_pcur[slot];
+        s.vcur = s.step_graph_vcur[slot];
         s.maxabs_slot = mslot0 ^ 1;
         s.sorted_slot = s.step_graph_sorted_slot[slot];
     }
@@ -1274,7 +1336,7 @@ void nbody_compute_colors(NBodySim& s, double max_speed)
 {
     B200_CHECK(cudaSetDevice(s.device));
     if (s.n > 0) {
-        colors_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.vel[s.cur], s.id[s.cur], s.colors, s.n, max_speed);
+        colors_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.vel[s.vcur], s.id[s.vcur], s.colors, s.n, max_speed);
         B200_CHECK(cudaGetLastError());
     }
 }
@@ -1283,7 +1345,7 @@ void nbody_get_positions(NBodySim& s, float* out)
 {
     B200_CHECK(cudaSetDevice(s.device));
     if (s.n == 0) return;
-    unpermute3_kernel<float><<<div_up(s.n, 256), 256, 0, s.stream>>>(s.pos[s.cur], s.id[s.cur], (float*)s.stage, s.n);
+    unpermute3_kernel<float><<<div_up(s.n, 256), 256, 0, s.stream>>>(s.pos[s.pcur], s.id[s.vcur], (float*)s.stage, s.n);
     B200_CHECK(cudaGetLastError());
     B200_CHECK(cudaMemcpyAsync(out, s.stage, 3 * (size_t)s.n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     sync_and_check(s);
@@ -1293,7 +1355,7 @@ void nbody_get_positions_f64(NBodySim& s, double* out)
 {
     B200_CHECK(cudaSetDevice(s.device));
     if (s.n == 0) return;
-    unpermute3_kernel<double><<<div_up(s.n, 256), 256, 0, s.stream>>>(s.pos[s.cur], s.id[s.cur], (double*)s.stage, s.n);
+    unpermute3_kernel<double><<<div_up(s.n, 256), 256, 0, s.stream>>>(s.pos[s.pcur], s.id[s.vcur], (double*)s.stage, s.n);
     B200_CHECK(cudaGetLastError());
     B200_CHECK(cudaMemcpyAsync(out, s.stage, 3 * (size_t)s.n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     sync_and_check(s);
@@ -1303,7 +1365,7 @@ void nbody_get_velocities(NBodySim& s, double* out)
 {
     B200_CHECK(cudaSetDevice(s.device));
     if (s.n == 0) return;
-    unpermute3_kernel<double><<<div_up(s.n, 256), 256, 0, s.stream>>>(s.vel[s.cur], s.id[s.cur], (double*)s.stage, s.n);
+    unpermute3_kernel<double><<<div_up(s.n, 256), 256, 0, s.stream>>>(s.vel[s.vcur], s.id[s.vcur], (double*)s.stage, s.n);
     B200_CHECK(cudaGetLastError());
     B200_CHECK(cudaMemcpyAsync(out, s.stage, 3 * (size_t)s.n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     sync_and_check(s);
@@ -1328,7 +1390,7 @@ void nbody_get_accelerations(NBodySim& s, float* out)
     nbody_traverse(s, 0, s.n);
     s.timer.enabled = timing;
     s.count_interactions = counting;
-    unpermute_acc_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.acc, s.id[s.cur], (float*)s.stage, s.n);
+    unpermute_acc_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.acc, s.id[s.vcur], (float*)s.stage, s.n);
     B200_CHECK(cudaGetLastError());
     B200_CHECK(cudaMemcpyAsync(out, s.stage, 3 * (size_t)s.n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
     sync_and_check(s);
@@ -1383,7 +1445,7 @@ void nbody_state_checksum(NBodySim& s, uint64_t out[2])
     if (s.n == 0) return;
     unsigned long long* d = reinterpret_cast<unsigned long long*>(s.stage);   // getter staging: free between calls
     B200_CHECK(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), s.stream));
-    checksum_kernel<<<min(div_up(s.n, 256), s.sm_count * 8), 256, 0, s.stream>>>(s.pos[s.cur], s.vel[s.cur], s.id[s.cur], s.n, d);
+    checksum_kernel<<<min(div_up(s.n, 256), s.sm_count * 8), 256, 0, s.stream>>>(s.pos[s.pcur], s.vel[s.vcur], s.id[s.vcur], s.n, d);
     B200_CHECK(cudaGetLastError());
     unsigned long long h[2] = {0, 0};
     B200_CHECK(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s.stream));
@@ -1405,7 +1467,7 @@ void nbody_get_perm(NBodySim& s, uint32_t* out)
     B200_CHECK(cudaSetDevice(s.device));
     if (s.n == 0) return;
     if (!s.tree_valid) nbody_build_tree(s);
-    B200_CHECK(cudaMemcpyAsync(out, s.id[s.cur], (size_t)s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+    B200_CHECK(cudaMemcpyAsync(out, s.id[s.vcur], (size_t)s.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
     sync_and_check(s);
 }
 
@@ -1539,7 +1601,7 @@ static void launch_frame(NBodySim& s, float* fpos, float* fcol, double max_speed
     const int n = s.n;
     cudaStream_t st = s.stream;
     if (n < s.unperm_min_n || !s.unperm_counts) {
-        frame_kernel<<<div_up(n, 256), 256, 0, st>>>(s.pos[s.cur], s.vel[s.cur], s.id[s.cur], fpos, fcol, n, max_speed);
+        frame_kernel<<<div_up(n, 256), 256, 0, st>>>(s.pos[s.pcur], s.vel[s.vcur], s.id[s.vcur], fpos, fcol, n, max_speed);
         ++s.launches;
     } else {
         int shift = s.unperm_shift;   // 2^20 creation indices per bucket (24 MB of output), more when n > 64 M
@@ -1549,8 +1611,8 @@ static void launch_frame(NBodySim& s, float* fpos, float* fcol, double max_speed
         s.tree_valid = false;
         B200_CHECK(cudaMemsetAsync(s.unperm_counts, 0, 2 * UNP_BUCKETS * sizeof(unsigned), st));
         const int blocks = div_up(n, 256 * UNP_ITEMS);
-        unperm_hist_kernel<<<blocks, 256, 0, st>>>(s.id[s.cur], n, shift, s.unperm_counts);
-        unperm_partition_kernel<<<blocks, 256, 0, st>>>(s.pos[s.cur], s.vel[s.cur], s.id[s.cur], n, shift, max_speed, s.unperm_counts,
+        unperm_hist_kernel<<<blocks, 256, 0, st>>>(s.id[s.vcur], n, shift, s.unperm_counts);
+        unperm_partition_kernel<<<blocks, 256, 0, st>>>(s.pos[s.pcur], s.vel[s.vcur], s.id[s.vcur], n, shift, max_speed, s.unperm_counts,
                                                         s.unperm_counts + UNP_BUCKETS, rec_a, rec_b);
         unperm_scatter_kernel<<<div_up(n, 256), 256, 0, st>>>(rec_a, rec_b, n, fpos, fcol);
         s.launches += 3;
@@ -1712,18 +1774,19 @@ void nbody_set_state_commit(NBodySim& s)
     B200_REQUIRE(s.upload_pending || s.n == 0, "set_state_commit without set_state_begin");
     if (s.n == 0) return;
     const size_t bytes = 3 * (size_t)s.n * sizeof(double);
-    const int o = s.cur ^ 1;
+    const int po = (s.pcur + 1) % 3, o = s.vcur ^ 1;
     // host-side wait: once commit returns the caller may reuse its host arrays (the copy was started a
     // step earlier, so this normally returns at once)
     B200_CHECK(cudaEventSynchronize(s.ev_upload_done));
-    B200_CHECK(cudaMemcpyAsync(s.pos[o], s.up_pos, bytes, cudaMemcpyDeviceToDevice, s.stream));
+    B200_CHECK(cudaMemcpyAsync(s.pos[po], s.up_pos, bytes, cudaMemcpyDeviceToDevice, s.stream));
     B200_CHECK(cudaMemcpyAsync(s.vel[o], s.up_vel, bytes, cudaMemcpyDeviceToDevice, s.stream));
     B200_CHECK(cudaEventRecord(s.ev_upload_consumed, s.stream));
     B200_CHECK(cudaMemcpyAsync(s.mass[o], s.mass0, (size_t)s.n * sizeof(double), cudaMemcpyDeviceToDevice, s.stream));
     iota_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.id[o], s.n);
     s.launches += 1;
     B200_CHECK(cudaGetLastError());
-    s.cur = o;
+    s.pcur = po;
+    s.vcur = o;
     recompute_maxabs(s);
     s.tree_valid = false;
     s.upload_pending = false;

@@ -49,12 +49,18 @@ struct NBodySim {
     double G = 0, softening = 0, damping = 1, theta = 0.5;
     cudaStream_t stream = nullptr;
 
-    double* pos[2] = {nullptr, nullptr};
+    // Master state.  Positions rotate through THREE buffers -- previous state (keygen / gather input) ->
+    // the same bodies in the new Morton order (written by the gather, read by the prefix sums and by the fused
+    // integration) -> next state (written by the traversal's epilogue, on every rank) -- so a peer GPU may
+    // already write step t's result while this GPU still reads step t's inputs.  Velocities, masses and ids
+    // alternate between two buffers; velocities are never reordered by a pass of their own.
+    double* pos[3] = {nullptr, nullptr, nullptr};
     double* vel[2] = {nullptr, nullptr};
     double* mass[2] = {nullptr, nullptr};
     double* mass0 = nullptr;                  // masses in creation order (what set_state restores without a scatter)
     uint32_t* id[2] = {nullptr, nullptr};
-    int cur = 0;
+    int pcur = 0, vcur = 0;                   // buffers holding the current state (pos / vel, mass, id)
+    bool step_pending = false;                // between a step's tree build and its fused traversal + integration
 
     uint64_t* keys[2] = {nullptr, nullptr};
     uint32_t* vals[2] = {nullptr, nullptr};
@@ -91,11 +97,12 @@ struct NBodySim {
     void* stage = nullptr;                    // (N,3) f64-sized staging for getters
     bool tree_valid = false;                  // keys/perm/tree describe the current positions
     // captured steps (nbody_step): CUDA graphs cached by (current buffer, parameters)
-    static constexpr int MAX_STEP_GRAPHS = 4;
-    cudaGraphExec_t step_graph[MAX_STEP_GRAPHS] = {nullptr, nullptr, nullptr, nullptr};
-    alignas(8) unsigned char step_graph_key[MAX_STEP_GRAPHS][80] = {};
-    int64_t step_graph_launches[MAX_STEP_GRAPHS] = {0, 0, 0, 0};
-    int step_graph_sorted_slot[MAX_STEP_GRAPHS] = {0, 0, 0, 0};
+    static constexpr int MAX_STEP_GRAPHS = 8;   // (3 position buffers x 2 velocity buffers: six graphs in steady state)
+    cudaGraphExec_t step_graph[MAX_STEP_GRAPHS] = {};
+    alignas(8) unsigned char step_graph_key[MAX_STEP_GRAPHS][96] = {};
+    int64_t step_graph_launches[MAX_STEP_GRAPHS] = {};
+    int step_graph_sorted_slot[MAX_STEP_GRAPHS] = {};
+    int step_graph_pcur[MAX_STEP_GRAPHS] = {}, step_graph_vcur[MAX_STEP_GRAPHS] = {};   // state buffers after the step
     unsigned step_graph_next = 0;
     bool use_graph = true;
     int trav_mode = 0;                        // 0: per launch (64 for large N and theta, else 32); 32 / 64: forced
@@ -137,9 +144,10 @@ void nbody_alloc(NBodySim& s, int n);
 void nbody_free(NBodySim& s);
 void nbody_upload(NBodySim& s, const double* pos, const double* vel, const double* mass);
 void nbody_upload_state(NBodySim& s, const double* pos, const double* vel);
-// keygen .. extract: leaves keys/perm/tree valid for the current positions
+// keygen .. extract: leaves keys/perm/tree valid for the current positions; the state is physically in the new
+// Morton order afterwards (positions, velocities, masses, ids)
 void nbody_build_tree(NBodySim& s);
-// traversal of sorted bodies [begin, end) into s.acc
+// traversal of sorted bodies [begin, end) into s.acc (forces only)
 void nbody_traverse(NBodySim& s, int begin, int end);
 // sharded sort: setup the exchange buffers; keygen + local sort of one slice; merge + rest of the tree
 void nbody_ms_setup(NBodySim& s, int slice, int world);

@@ -58,16 +58,63 @@ __device__ __forceinline__ void mac_pair(float2 d2, float T0, float T1, bool in,
     r.y = a1 ? rsqrt_approx(d2.y) : 0.f;
 }
 
-template <bool COUNT>
+// ---------------------------------------------------------------------------- fused integrate + broadcast
+// The warp that has just finished the forces of a tile also finishes the step for its bodies: it fetches the
+// body's velocity through the sort permutation (the velocities are never reordered by a pass of their own),
+// applies v = (v + a dt) damping, x += v dt (nbody/simulation.py:281-305) in fp64 and writes the new state at the
+// body's NEW sorted position into the next-state buffers of EVERY rank -- its own and, over NVLink peer
+// mappings, the other GPUs' -- so with several GPUs the position exchange rides inside the compute-bound
+// traversal instead of following it as a collective.  The next step's max |coord| is reduced on the way.
+constexpr int TRAV_MAX_PEERS = 8;
+struct StepOut {
+    const uint32_t* perm;          // sorted position -> position in the previous order
+    const double* vel_prev;        // previous order
+    const double* pos_new;         // sorted order (gathered by the tree build)
+    double* pos_out[TRAV_MAX_PEERS];   // next-state buffers, sorted order; [0 .. world)
+    double* vel_out[TRAV_MAX_PEERS];
+    int world;
+    double dt, damping;
+    unsigned long long* maxabs;    // bit pattern of max |coord| over the bodies this launch integrated
+};
+
+__device__ __forceinline__ void finish_body(const StepOut& o, int k, float ax, float ay, float az, double& m)
+{
+    const int64_t j = 3 * (int64_t)o.perm[k], w = 3 * (int64_t)k;
+    const double a3[3] = {(double)ax, (double)ay, (double)az};
+    double v[3], x[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        v[d] = o.vel_prev[j + d];
+        v[d] += a3[d] * o.dt;
+        v[d] *= o.damping;
+        x[d] = o.pos_new[w + d] + v[d] * o.dt;
+        m = fmax(m, fabs(x[d]));
+    }
+    for (int r = 0; r < o.world; ++r) {
+        double* __restrict__ po = o.pos_out[r];
+        double* __restrict__ vo = o.vel_out[r];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { po[w + d] = x[d]; vo[w + d] = v[d]; }
+    }
+}
+
+__device__ __forceinline__ void finish_warp(const StepOut& o, double m)
+{
+    for (int s = 16; s > 0; s >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if (lane_id() == 0) atomicMax(o.maxabs, (unsigned long long)__double_as_longlong(m));
+}
+
+template <bool COUNT, bool INTEG>
 __global__ void __launch_bounds__(TRAV_BLOCK, 4) traverse_kernel(const float4* __restrict__ recs, const float4* __restrict__ posm,
                                                                  float4* __restrict__ acc, int tile_begin, int tile_end, int n,
                                                                  float eps2, float G, unsigned* tile_counter,
-                                                                 unsigned long long* counters, unsigned* error)
+                                                                 unsigned long long* counters, unsigned* error, const StepOut so)
 {
     extern __shared__ __align__(16) unsigned char trav_smem[];
     const unsigned lane = lane_id();
     const unsigned lanebit = 1u << lane;
     const unsigned lt = lanemask_lt();
+    double w_maxabs = 0.0;
     WarpShared& ws = reinterpret_cast<WarpShared*>(trav_smem)[threadIdx.x >> 5];
     const float4* sXY = ws.stage;
     const float4* sZM = ws.stage + TRAV_AREA;
@@ -213,7 +260,11 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 4) traverse_kernel(const float4* _
             __syncwarp();
         }
         // acc.w: exact interaction count (COUNT) or the tile's evaluated pair slots (a cost proxy)
-        if (valid) acc[k] = make_float4(G * (ax.x + ax.y), G * (ay.x + ay.y), G * (az.x + az.y), __int_as_float(COUNT ? cnt : slots));
+        if (valid) {
+            const float fx = G * (ax.x + ax.y), fy = G * (ay.x + ay.y), fz = G * (az.x + az.y);
+            acc[k] = make_float4(fx, fy, fz, __int_as_float(COUNT ? cnt : slots));
+            if (INTEG) finish_body(so, k, fx, fy, fz, w_maxabs);
+        }
         if (COUNT) {
             unsigned c32 = valid ? (unsigned)cnt : 0u, l32 = (unsigned)lanepairs;
             for (int o = 16; o > 0; o >>= 1) {
@@ -225,6 +276,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 4) traverse_kernel(const float4* _
             w_slots += (unsigned)slots;
         }
     }
+    if (INTEG) finish_warp(so, w_maxabs);
     if (COUNT && lane == 0) {
         if (w_inter) atomicAdd(&counters[0], w_inter);
         atomicAdd(&counters[1], w_slots);
@@ -234,30 +286,11 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 4) traverse_kernel(const float4* _
     }
 }
 
-// ---------------------------------------------------------------------------- 64-body walk
-// The same walk with TWO bodies per lane: a warp owns 64 consecutive sorted bodies (lane l: bodies l
-// and l + 32 of the tile), a stack entry carries one lane mask per 32-body half.  A staged pair
-// record is read from shared memory once for both halves and the batch bookkeeping is shared, which
-// halves the shared-memory wavefronts and the walk overhead per evaluated pair.  A batch is sorted by
-// class -- pairs needed by both halves, only by the low half, only by the high half -- and each class
-// has its own loop, so a half never evaluates a pair none of its lanes asked for: the evaluated
-// (pair, half) set is exactly that of two independent 32-body walks, every lane still makes the
-// reference's per-body MAC decision.
-#ifndef TRAV64_UNROLL_BOTH
-#define TRAV64_UNROLL_BOTH 2
-#endif
-#ifndef TRAV64_UNROLL_ONE
-#define TRAV64_UNROLL_ONE 4
-#endif
-constexpr int U64_BOTH = TRAV64_UNROLL_BOTH, U64_ONE = TRAV64_UNROLL_ONE;   // eval loop unroll factors
-struct __align__(16) WarpShared64 {
-    unsigned stk_first[TRAV_CAP];        // pair index | (pairs - 1) << 29 (one pair, except chunks of a bucket)
-    unsigned stk_lo[TRAV_CAP];           // lanes whose body l opened the pair's parent cell
-    unsigned stk_hi[TRAV_CAP];           //                 body l + 32
-    float4 stage[5 * TRAV_AREA];         // XY ZM {T0,T1,mask lo,mask hi} FN {open lo 0, lo 1, hi 0, hi 1}
-};
-constexpr size_t TRAV64_SMEM_BYTES = sizeof(WarpShared64) * TRAV_WARPS;
-
+// ---------------------------------------------------------------------------- two bodies per lane
+// A warp owns 64 consecutive sorted bodies (lane l: bodies l and l + 32 of the tile), a stack entry carries
+// one lane mask per 32-body half.  A staged pair record is read from shared memory once for both halves and
+// the batch bookkeeping is shared.  The evaluated (pair, half) set is exactly that of two independent 32-body
+// walks; every lane still makes the reference's per-body MAC decision.
 struct EvalBody {
     float npx, npy, npz;                 // -position
     float2 ax, ay, az;                   // (even, odd) children accumulate separately
@@ -286,213 +319,6 @@ __device__ __forceinline__ void eval_pair(const float4& XY, const float4& ZM, fl
     b.ax = __ffma2_rn(dx, f, b.ax);
     b.ay = __ffma2_rn(dy, f, b.ay);
     b.az = __ffma2_rn(dz, f, b.az);
-}
-
-template <bool COUNT>
-__global__ void __launch_bounds__(TRAV_BLOCK, 3) traverse64_kernel(const float4* __restrict__ recs, const float4* __restrict__ posm,
-                                                                   float4* __restrict__ acc, int begin, int end,
-                                                                   float eps2, float G, unsigned* tile_counter,
-                                                                   unsigned long long* counters, unsigned* error)
-{
-    extern __shared__ __align__(16) unsigned char trav_smem[];
-    const unsigned lane = lane_id();
-    const unsigned lanebit = 1u << lane;
-    const unsigned lt = lanemask_lt();
-    WarpShared64& ws = reinterpret_cast<WarpShared64*>(trav_smem)[threadIdx.x >> 5];
-    const float4* sXY = ws.stage;
-    const float4* sZM = ws.stage + TRAV_AREA;
-    const float4* sTM = ws.stage + 2 * TRAV_AREA;
-    const float4* sFN = ws.stage + 3 * TRAV_AREA;
-    uint4* sOP = reinterpret_cast<uint4*>(ws.stage + 4 * TRAV_AREA);
-    const float2 eps22 = make_float2(eps2, eps2);
-    unsigned long long w_inter = 0, w_slots = 0, w_lanepairs = 0, w_batches = 0, w_both = 0;
-    int w_spmax = 0;
-
-    for (;;) {
-        unsigned t = 0;
-        if (lane == 0) t = atomicAdd(tile_counter, 1u);
-        t = __reduce_max_sync(0xffffffffu, t);   // (broadcast through a uniform register: the compiler can prove the walk convergent)
-        const int64_t base = (int64_t)begin + 64 * (int64_t)t;
-        if (base >= end) break;
-        const int ka = (int)base + (int)lane, kb = ka + 32;
-        const bool va = ka < end, vb = kb < end;
-        EvalBody A, B;
-        {
-            const float4 pa = va ? posm[ka] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 pb = vb ? posm[kb] : make_float4(0.f, 0.f, 0.f, 0.f);
-            A.npx = -pa.x; A.npy = -pa.y; A.npz = -pa.z;
-            B.npx = -pb.x; B.npy = -pb.y; B.npz = -pb.z;
-        }
-        A.ax = A.ay = A.az = B.ax = B.ay = B.az = make_float2(0.f, 0.f);
-        A.cnt = A.lanepairs = B.cnt = B.lanepairs = 0;
-        int slots_a = 0, slots_b = 0;
-        {
-            const unsigned vma = __ballot_sync(0xffffffffu, va), vmb = __ballot_sync(0xffffffffu, vb);
-            if (lane == 0) { ws.stk_first[0] = 0u; ws.stk_lo[0] = vma; ws.stk_hi[0] = vmb; }   // pair 0 = {root, dummy}
-        }
-        int sp = 1;
-        __syncwarp();
-        while (sp > 0) {
-            // ---- select: the top entries, one per lane, sorted by class (both | low only | high only)
-            const int idx = sp - 1 - (int)lane;
-            unsigned ef = 0, ml = 0, mh = 0;
-            if (idx >= 0) { ef = ws.stk_first[idx]; ml = ws.stk_lo[idx]; mh = ws.stk_hi[idx]; }
-            const unsigned multi = __ballot_sync(0xffffffffu, (ef >> 29) != 0u);
-            const bool chunk = (multi & 1u) != 0u;
-            const unsigned ef0 = __shfl_sync(0xffffffffu, ef, 0);
-            const unsigned ml0 = __shfl_sync(0xffffffffu, ml, 0), mh0 = __shfl_sync(0xffffffffu, mh, 0);
-            const int room = (TRAV_CAP - TRAV_RESERVE - sp) / 7;
-            int E = min(min(sp, TRAV_BATCH), max(room, 1));
-            if (multi) E = min(E, __ffs(multi) - 1);
-            const bool taken = (int)lane < E;
-            const unsigned bB = __ballot_sync(0xffffffffu, taken && ml != 0u && mh != 0u);
-            const unsigned bL = __ballot_sync(0xffffffffu, taken && mh == 0u);
-            int nB = __popc(bB), nL = __popc(bL), P = E;
-            int slot = (bB & lanebit) ? __popc(bB & lt) : (bL & lanebit) ? nB + __popc(bL & lt) : nB + nL + (int)lane - __popc((bB | bL) & lt);
-            if (chunk) {   // a chunk of a bucket is a batch of its own: P pairs of one class
-                E = 1;
-                P = (int)(ef0 >> 29) + 1;
-                nB = (ml0 != 0u && mh0 != 0u) ? P : 0;
-                nL = (mh0 == 0u) ? P : 0;
-            }
-            // (the max-reduces leave the trip counts in uniform registers: the loops below are provably convergent)
-            P = __reduce_max_sync(0xffffffffu, P);
-            nB = __reduce_max_sync(0xffffffffu, nB);
-            nL = __reduce_max_sync(0xffffffffu, nL);
-            const int top = sp - 1;
-            sp -= E;
-            // ---- load: 8 pair records (4 x 16 B each) per warp-wide load; entry e goes to its class slot
-#pragma unroll
-            for (int it = 0; it < TRAV_BATCH / 8; ++it) {
-                const int e = it * 8 + (int)(lane >> 2);
-                int sl = __shfl_sync(0xffffffffu, slot, e);
-                if (e < P) {
-                    unsigned first, mlo, mhi;
-                    if (chunk) { first = (ef0 & TRAV_FIRST_MASK) + (unsigned)e; mlo = ml0; mhi = mh0; sl = e; }
-                    else { first = ws.stk_first[top - e]; mlo = ws.stk_lo[top - e]; mhi = ws.stk_hi[top - e]; }
-                    float4 v = __ldg(&recs[4 * (int64_t)first + (lane & 3u)]);
-                    if ((lane & 3u) == 2u) { v.z = __uint_as_float(mlo); v.w = __uint_as_float(mhi); }
-                    ws.stage[(lane & 3u) * TRAV_AREA + sl] = v;
-                }
-            }
-            __syncwarp();
-            // ---- eval, one loop per class
-            const int jL = nB + nL;
-#pragma unroll U64_BOTH
-            for (int j = 0; j < nB; ++j) {
-                const float4 XY = sXY[j];
-                const float4 ZM = sZM[j];
-                const float4 TM = sTM[j];
-                uint4 om;
-                eval_pair<COUNT>(XY, ZM, TM.x, TM.y, __float_as_uint(TM.z), lanebit, eps22, A, om.x, om.y);
-                eval_pair<COUNT>(XY, ZM, TM.x, TM.y, __float_as_uint(TM.w), lanebit, eps22, B, om.z, om.w);
-                if (lane == 0) sOP[j] = om;
-            }
-#pragma unroll U64_ONE
-            for (int j = nB; j < jL; ++j) {
-                const float4 XY = sXY[j];
-                const float4 ZM = sZM[j];
-                const float4 TM = sTM[j];
-                uint4 om = make_uint4(0u, 0u, 0u, 0u);
-                eval_pair<COUNT>(XY, ZM, TM.x, TM.y, __float_as_uint(TM.z), lanebit, eps22, A, om.x, om.y);
-                if (lane == 0) sOP[j] = om;
-            }
-#pragma unroll U64_ONE
-            for (int j = jL; j < P; ++j) {
-                const float4 XY = sXY[j];
-                const float4 ZM = sZM[j];
-                const float4 TM = sTM[j];
-                uint4 om = make_uint4(0u, 0u, 0u, 0u);
-                eval_pair<COUNT>(XY, ZM, TM.x, TM.y, __float_as_uint(TM.w), lanebit, eps22, B, om.z, om.w);
-                if (lane == 0) sOP[j] = om;
-            }
-            slots_a += jL;
-            slots_b += nB + (P - jL);
-            __syncwarp();
-            // ---- expand: lane j owns pair slot j
-            unsigned f0 = 0, f1 = 0, n0 = 0, n1 = 0;
-            uint4 om = make_uint4(0u, 0u, 0u, 0u);
-            if ((int)lane < P) {
-                om = sOP[lane];
-                const float4 tm = sTM[lane];   // the ballots include the lanes outside the masks
-                om.x &= __float_as_uint(tm.z); om.y &= __float_as_uint(tm.z);
-                om.z &= __float_as_uint(tm.w); om.w &= __float_as_uint(tm.w);
-                const float4 fn = sFN[lane];
-                f0 = __float_as_uint(fn.x); f1 = __float_as_uint(fn.y);
-                n0 = __float_as_uint(fn.z); n1 = __float_as_uint(fn.w);
-            }
-            const bool c0 = (om.x | om.z) != 0u && n0 != 0u, c1 = (om.y | om.w) != 0u && n1 != 0u;
-            const int np0 = c0 ? (int)((n0 + 1u) >> 1) : 0, np1 = c1 ? (int)((n1 + 1u) >> 1) : 0;
-            const bool big = np0 > TRAV_CELL_PAIRS || np1 > TRAV_CELL_PAIRS;
-            if (!__any_sync(0xffffffffu, big)) {
-                const unsigned k = (unsigned)(np0 + np1);
-                const unsigned b0 = __ballot_sync(0xffffffffu, (k & 1u) != 0u), b1 = __ballot_sync(0xffffffffu, (k & 2u) != 0u);
-                const unsigned b2 = __ballot_sync(0xffffffffu, (k & 4u) != 0u), b3 = __ballot_sync(0xffffffffu, (k & 8u) != 0u);
-                const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
-                if (sp + total > TRAV_CAP) {   // cannot happen (see the stack bound above); never drop silently
-                    if (lane == 0) atomicOr(error, (unsigned)ERR_STACK_OVERFLOW);
-                    sp = 0;
-                } else {
-                    int pos = sp + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) + 8 * __popc(b3 & lt);
-                    for (int q = 0; q < np0; ++q, ++pos) { ws.stk_first[pos] = f0 + (unsigned)q; ws.stk_lo[pos] = om.x; ws.stk_hi[pos] = om.z; }
-                    for (int q = 0; q < np1; ++q, ++pos) { ws.stk_first[pos] = f1 + (unsigned)q; ws.stk_lo[pos] = om.y; ws.stk_hi[pos] = om.w; }
-                    sp += total;
-                }
-            } else {
-                // rare: a bucket of > 8 bodies sharing one finest-level cell is pushed in chunks of <= 8 pairs
-                const int e0 = (np0 + TRAV_CHUNK_PAIRS - 1) / TRAV_CHUNK_PAIRS;
-                const int e1 = (np1 + TRAV_CHUNK_PAIRS - 1) / TRAV_CHUNK_PAIRS;
-                int inc2 = e0 + e1;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int u = __shfl_up_sync(0xffffffffu, inc2, o);
-                    if ((int)lane >= o) inc2 += u;
-                }
-                const int total = __reduce_add_sync(0xffffffffu, e0 + e1);
-                if (sp + total > TRAV_CAP) {   // never drop silently
-                    if (lane == 0) atomicOr(error, (unsigned)ERR_STACK_OVERFLOW);
-                    sp = 0;
-                } else {
-                    int pos = sp + inc2 - (e0 + e1);
-                    for (int q = 0; q < e0; ++q, ++pos) {
-                        const int r = min(np0 - TRAV_CHUNK_PAIRS * q, TRAV_CHUNK_PAIRS);
-                        ws.stk_first[pos] = (f0 + (unsigned)(TRAV_CHUNK_PAIRS * q)) | ((unsigned)(r - 1) << 29);
-                        ws.stk_lo[pos] = om.x; ws.stk_hi[pos] = om.z;
-                    }
-                    for (int q = 0; q < e1; ++q, ++pos) {
-                        const int r = min(np1 - TRAV_CHUNK_PAIRS * q, TRAV_CHUNK_PAIRS);
-                        ws.stk_first[pos] = (f1 + (unsigned)(TRAV_CHUNK_PAIRS * q)) | ((unsigned)(r - 1) << 29);
-                        ws.stk_lo[pos] = om.y; ws.stk_hi[pos] = om.w;
-                    }
-                    sp += total;
-                }
-            }
-            sp = __reduce_max_sync(0xffffffffu, sp);   // uniform register: the walk loop is provably convergent
-            if (COUNT) { ++w_batches; w_both += (unsigned)nB; w_spmax = max(w_spmax, sp); }
-            __syncwarp();
-        }
-        // acc.w: exact interaction count (COUNT) or the half-tile's evaluated pair slots (a cost proxy)
-        if (va) acc[ka] = make_float4(G * (A.ax.x + A.ax.y), G * (A.ay.x + A.ay.y), G * (A.az.x + A.az.y), __int_as_float(COUNT ? A.cnt : slots_a));
-        if (vb) acc[kb] = make_float4(G * (B.ax.x + B.ax.y), G * (B.ay.x + B.ay.y), G * (B.az.x + B.az.y), __int_as_float(COUNT ? B.cnt : slots_b));
-        if (COUNT) {
-            unsigned c32 = (va ? (unsigned)A.cnt : 0u) + (vb ? (unsigned)B.cnt : 0u), l32 = (unsigned)(A.lanepairs + B.lanepairs);
-            for (int o = 16; o > 0; o >>= 1) {
-                c32 += __shfl_xor_sync(0xffffffffu, c32, o);
-                l32 += __shfl_xor_sync(0xffffffffu, l32, o);
-            }
-            w_inter += c32;
-            w_lanepairs += l32;
-            w_slots += (unsigned)(slots_a + slots_b);
-        }
-    }
-    if (COUNT && lane == 0) {
-        if (w_inter) atomicAdd(&counters[0], w_inter);
-        atomicAdd(&counters[1], w_slots);
-        atomicAdd(&counters[2], w_lanepairs);
-        atomicAdd(&counters[3], w_batches);
-        atomicMax(&counters[4], (unsigned long long)w_spmax);
-        atomicAdd(&counters[5], w_both);
-    }
 }
 
 // ---------------------------------------------------------------------------- 64-body walk, classed
@@ -556,12 +382,13 @@ __device__ __forceinline__ void eval_sure(const float4& XY, const float4& ZM, bo
     }
 }
 
-template <bool COUNT>
+template <bool COUNT, bool INTEG>
 __global__ void __launch_bounds__(TRAV_BLOCK, 3) traverse64c_kernel(const float4* __restrict__ recs, const float4* __restrict__ posm,
                                                                     float4* __restrict__ acc, int begin, int end,
                                                                     float eps2, float G, unsigned* tile_counter,
-                                                                    unsigned long long* counters, unsigned* error)
+                                                                    unsigned long long* counters, unsigned* error, const StepOut so)
 {
+    double w_maxabs = 0.0;
     extern __shared__ __align__(16) unsigned char trav_smem[];
     const unsigned lane = lane_id();
     const unsigned lanebit = 1u << lane;
@@ -794,8 +621,16 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 3) traverse64c_kernel(const float4
             __syncwarp();
         }
         // acc.w: exact interaction count (COUNT) or the half-tile's evaluated pair slots (a cost proxy)
-        if (va) acc[ka] = make_float4(G * (A.ax.x + A.ax.y), G * (A.ay.x + A.ay.y), G * (A.az.x + A.az.y), __int_as_float(COUNT ? A.cnt : slots_a));
-        if (vb) acc[kb] = make_float4(G * (B.ax.x + B.ax.y), G * (B.ay.x + B.ay.y), G * (B.az.x + B.az.y), __int_as_float(COUNT ? B.cnt : slots_b));
+        if (va) {
+            const float fx = G * (A.ax.x + A.ax.y), fy = G * (A.ay.x + A.ay.y), fz = G * (A.az.x + A.az.y);
+            acc[ka] = make_float4(fx, fy, fz, __int_as_float(COUNT ? A.cnt : slots_a));
+            if (INTEG) finish_body(so, ka, fx, fy, fz, w_maxabs);
+        }
+        if (vb) {
+            const float fx = G * (B.ax.x + B.ax.y), fy = G * (B.ay.x + B.ay.y), fz = G * (B.az.x + B.az.y);
+            acc[kb] = make_float4(fx, fy, fz, __int_as_float(COUNT ? B.cnt : slots_b));
+            if (INTEG) finish_body(so, kb, fx, fy, fz, w_maxabs);
+        }
         if (COUNT) {
             unsigned c32 = (va ? (unsigned)A.cnt : 0u) + (vb ? (unsigned)B.cnt : 0u), l32 = (unsigned)(A.lanepairs + B.lanepairs);
             for (int o = 16; o > 0; o >>= 1) {
@@ -807,6 +642,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 3) traverse64c_kernel(const float4
             w_slots += (unsigned)(slots_a + slots_b);
         }
     }
+    if (INTEG) finish_warp(so, w_maxabs);
     if (COUNT && lane == 0) {
         if (w_inter) atomicAdd(&counters[0], w_inter);
         atomicAdd(&counters[1], w_slots);
