@@ -11,8 +11,24 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 }  // namespace b200
 
 struct b200_nbody {
-    b200::NBodySim sim;
+    b200::NBodySim sim;                        // the (primary) replica: getters, frames, stats
+    std::vector<b200::NBodySim*> others;       // further replicas of a device-mask handle (one process, several GPUs)
+    b200::NBodyGroup* group = nullptr;         // set by comm_init / create_multi: step() is the sharded fused step
 };
+
+// device-mask handles: a getter that rebuilds the tree reorders the state of the replica it runs on; the other
+// replicas must follow, or the ranks would disagree on which state buffer is current
+static void rebuild_other_replicas(b200_nbody* h)
+{
+    for (b200::NBodySim* o : h->others)
+        if (!o->tree_valid) b200::nbody_build_tree(*o);
+}
+
+static void step_any(b200_nbody* h, double dt)
+{
+    if (h->group) b200::group_step(*h->group, dt);
+    else b200::nbody_step(h->sim, dt);
+}
 struct b200_boids {
     b200::BoidsSim sim;
 };
@@ -98,29 +114,100 @@ B200_API int b200_nbody_create(int64_t n, const double* pos, const double* vel, 
 B200_API int b200_nbody_destroy(b200_nbody* h)
 {
     if (!h) return B200_OK;
+    if (h->group) b200::group_destroy(h->group);
+    h->group = nullptr;
+    for (b200::NBodySim* o : h->others) { b200::nbody_free(*o); delete o; }
     b200::nbody_free(h->sim);
     delete h;
+    return B200_OK;
+}
+
+B200_API int b200_nccl_unique_id(void* out128)
+{
+    B200_ARG(out128, "null argument");
+    B200_TRY(b200::nccl_unique_id(out128))
+}
+
+B200_API int b200_nbody_comm_init(b200_nbody* h, const void* id128, int rank, int world)
+{
+    B200_ARG(h && id128, "null argument");
+    B200_ARG(!h->group, "the handle already belongs to a group");
+    B200_ARG(world >= 1 && world <= b200::SHARD_MAX_WORLD && rank >= 0 && rank < world, "bad rank / world (at most 8 ranks)");
+    B200_TRY(h->group = b200::group_create_rank(h->sim, id128, rank, world))
+}
+
+B200_API int b200_nbody_world(b200_nbody* h, int* world)
+{
+    B200_ARG(h && world, "null argument");
+    *world = b200::group_world(h->group);
+    return B200_OK;
+}
+
+B200_API int b200_nbody_create_multi(int64_t n, const double* pos, const double* vel, const double* mass, double G,
+                                     double softening, double damping, double theta, uint32_t device_mask, b200_nbody** out)
+{
+    B200_ARG(out, "out handle is null");
+    *out = nullptr;
+    B200_ARG(n >= 0 && n < (int64_t)1 << 30, "n out of range [0, 2^30)");
+    B200_ARG(n == 0 || (pos && vel && mass), "pos/vel/mass is null");
+    B200_ARG(theta >= 0.0, "theta must be >= 0");
+    B200_ARG(device_mask != 0u, "empty device mask");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) ndev = 0;
+    std::vector<int> devs;
+    for (int d = 0; d < 32; ++d)
+        if (device_mask & (1u << d)) {
+            B200_ARG(d < ndev, "device mask names a device that does not exist");
+            devs.push_back(d);
+        }
+    B200_ARG((int)devs.size() <= b200::SHARD_MAX_WORLD, "at most 8 devices");
+    b200_nbody* h = new b200_nbody();
+    try {
+        std::vector<b200::NBodySim*> sims;
+        for (size_t i = 0; i < devs.size(); ++i) {
+            b200::NBodySim* s = &h->sim;
+            if (i > 0) { s = new b200::NBodySim(); h->others.push_back(s); }
+            s->device = devs[i];
+            s->G = G; s->softening = softening; s->damping = damping; s->theta = theta;
+            b200::nbody_alloc(*s, (int)n);
+            b200::nbody_upload(*s, pos, vel, mass);
+            sims.push_back(s);
+        }
+        if (sims.size() > 1) h->group = b200::group_create_local(sims);
+    } catch (const b200::CudaError& e) {
+        b200::set_error(e.msg);
+        b200_nbody_destroy(h);
+        return B200_ERR_CUDA;
+    } catch (const b200::StateError& e) {
+        b200::set_error(e.msg);
+        b200_nbody_destroy(h);
+        return B200_ERR_STATE;
+    }
+    *out = h;
     return B200_OK;
 }
 
 B200_API int b200_nbody_step(b200_nbody* h, double dt)
 {
     B200_ARG(h, "handle is null");
-    B200_TRY(b200::nbody_step(h->sim, dt))
+    B200_TRY(step_any(h, dt))
 }
 
 B200_API int b200_nbody_step_n(b200_nbody* h, double dt, int nsteps)
 {
     B200_ARG(h, "handle is null");
     B200_TRY({
-        for (int i = 0; i < nsteps; ++i) b200::nbody_step(h->sim, dt);
+        for (int i = 0; i < nsteps; ++i) step_any(h, dt);
     })
 }
 
 B200_API int b200_nbody_compute_accelerations(b200_nbody* h, float* out)
 {
     B200_ARG(h && (out || h->sim.n == 0), "null argument");
-    B200_TRY(b200::nbody_get_accelerations(h->sim, out))
+    B200_TRY({
+        rebuild_other_replicas(h);
+        b200::nbody_get_accelerations(h->sim, out);
+    })
 }
 
 B200_API int b200_nbody_compute_colors(b200_nbody* h, double max_speed)
@@ -157,6 +244,11 @@ B200_API int b200_nbody_sync(b200_nbody* h)
 {
     B200_ARG(h, "handle is null");
     B200_TRY({
+        for (b200::NBodySim* o : h->others) {
+            B200_CHECK(cudaSetDevice(o->device));
+            B200_CHECK(cudaStreamSynchronize(o->stream));
+            b200::nbody_check_errors(*o);
+        }
         B200_CHECK(cudaSetDevice(h->sim.device));
         B200_CHECK(cudaStreamSynchronize(h->sim.stream));
         b200::nbody_check_errors(h->sim);   // never return truncated forces silently
@@ -166,31 +258,45 @@ B200_API int b200_nbody_sync(b200_nbody* h)
 B200_API int b200_nbody_set_state(b200_nbody* h, const double* pos, const double* vel)
 {
     B200_ARG(h && ((pos && vel) || h->sim.n == 0), "null argument");
-    B200_TRY(b200::nbody_upload_state(h->sim, pos, vel))
+    B200_TRY({
+        for (b200::NBodySim* o : h->others) b200::nbody_upload_state(*o, pos, vel);
+        b200::nbody_upload_state(h->sim, pos, vel);
+        b200::group_state_replaced(h->group);
+    })
 }
 
 B200_API int b200_nbody_set_params(b200_nbody* h, double G, double softening, double damping, double theta)
 {
     B200_ARG(h, "handle is null");
     B200_ARG(theta >= 0.0, "theta must be >= 0");
-    h->sim.G = G;
-    h->sim.softening = softening;
-    h->sim.damping = damping;
-    h->sim.theta = theta;
-    h->sim.tree_valid = false;
+    std::vector<b200::NBodySim*> all(h->others);
+    all.push_back(&h->sim);
+    for (b200::NBodySim* s : all) {
+        s->G = G;
+        s->softening = softening;
+        s->damping = damping;
+        s->theta = theta;
+        s->tree_valid = false;
+    }
     return B200_OK;
 }
 
 B200_API int b200_nbody_get_keys(b200_nbody* h, uint64_t* out)
 {
     B200_ARG(h && (out || h->sim.n == 0), "null argument");
-    B200_TRY(b200::nbody_get_keys(h->sim, out))
+    B200_TRY({
+        rebuild_other_replicas(h);
+        b200::nbody_get_keys(h->sim, out);
+    })
 }
 
 B200_API int b200_nbody_get_perm(b200_nbody* h, uint32_t* out)
 {
     B200_ARG(h && (out || h->sim.n == 0), "null argument");
-    B200_TRY(b200::nbody_get_perm(h->sim, out))
+    B200_TRY({
+        rebuild_other_replicas(h);
+        b200::nbody_get_perm(h->sim, out);
+    })
 }
 
 B200_API int b200_nbody_get_stats(b200_nbody* h, b200_nbody_stats* out)
@@ -258,7 +364,10 @@ B200_API int b200_nbody_set_counting(b200_nbody* h, int enabled)
 B200_API int b200_nbody_count_interactions(b200_nbody* h, int64_t* interactions)
 {
     B200_ARG(h && interactions, "null argument");
-    B200_TRY(*interactions = b200::nbody_count_interactions(h->sim))
+    B200_TRY({
+        rebuild_other_replicas(h);
+        *interactions = b200::nbody_count_interactions(h->sim);
+    })
 }
 
 B200_API int b200_nbody_state_checksum(b200_nbody* h, uint64_t out[2])
@@ -277,7 +386,8 @@ B200_API int b200_nbody_timed_steps(b200_nbody* h, double dt, int nsteps, float*
         B200_CHECK(cudaEventCreate(&e0));
         B200_CHECK(cudaEventCreate(&e1));
         B200_CHECK(cudaEventRecord(e0, s.stream));
-        for (int i = 0; i < nsteps; ++i) b200::nbody_step(s, dt);
+        for (int i = 0; i < nsteps; ++i) step_any(h, dt);
+        B200_CHECK(cudaSetDevice(s.device));
         B200_CHECK(cudaEventRecord(e1, s.stream));
         B200_CHECK(cudaEventSynchronize(e1));
         B200_CHECK(cudaEventElapsedTime(elapsed_ms, e0, e1));
@@ -355,7 +465,11 @@ B200_API int b200_nbody_frame_begin_rows(b200_nbody* h, double max_speed, float*
 B200_API int b200_nbody_set_state_commit(b200_nbody* h)
 {
     B200_ARG(h, "handle is null");
-    B200_TRY(b200::nbody_set_state_commit(h->sim))
+    B200_ARG(h->others.empty(), "the asynchronous state prefetch is not available on a device-mask handle (use set_state)");
+    B200_TRY({
+        b200::nbody_set_state_commit(h->sim);
+        b200::group_state_replaced(h->group);
+    })
 }
 
 B200_API int b200_nbody_set_stream(b200_nbody* h, void* cuda_stream, int external)

@@ -1164,6 +1164,66 @@ static void step_fused(NBodySim& s, double dt)
     }
 }
 
+// ---------------------------------------------------------------------------- sharded fused step (pieces)
+void nbody_shard_build(NBodySim& s, bool presorted)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    if (s.n == 0) return;
+    if (presorted) {
+        B200_REQUIRE(s.ms_keys, "sharded sort is not set up");
+        cudaStream_t st = s.stream;
+        const int tiles_per_run = div_up(s.ms_slice, MERGE_TILE);
+        merge_runs_kernel<<<tiles_per_run * s.ms_world, 256, 0, st>>>(s.ms_keys, s.ms_vals, s.ms_slice, s.ms_world, s.n, tiles_per_run,
+                                                                      s.keys[0], s.vals[0]);
+        ++s.launches;
+        B200_CHECK(cudaGetLastError());
+        s.sorted_slot = 0;
+        build_after_sort(s, true);
+    } else {
+        build_tree_impl(s, true);
+    }
+}
+
+unsigned long long* nbody_shard_maxabs_next(NBodySim& s) { return s.d_maxabs + (s.maxabs_slot ^ 1); }
+
+void nbody_shard_traverse(NBodySim& s, double dt, const ShardPeers& peers)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    if (s.n == 0) return;
+    cudaStream_t st = s.stream;
+    const int gp = (s.pcur + 1) % 3, np = (s.pcur + 2) % 3, o = s.vcur ^ 1;
+    B200_CHECK(cudaMemsetAsync(nbody_shard_maxabs_next(s), 0, sizeof(unsigned long long), st));
+    StepOut so{};
+    so.perm = s.vals[s.sorted_slot];
+    so.vel_prev = s.vel[s.vcur];
+    so.pos_new = s.pos[gp];
+    B200_REQUIRE(peers.world >= 1 && peers.world <= TRAV_MAX_PEERS, "too many ranks for the fused broadcast");
+    for (int r = 0; r < peers.world; ++r) { so.pos_out[r] = peers.pos[r][np]; so.vel_out[r] = peers.vel[r][o]; }
+    so.world = peers.world;
+    so.dt = dt;
+    so.damping = s.damping;
+    so.maxabs = nbody_shard_maxabs_next(s);
+    traverse_launch(s, s.shard_begin, s.shard_end, &so);
+}
+
+void nbody_shard_finish(NBodySim& s)
+{
+    if (s.n > 0) {
+        s.timer.mark(s.stream);   // exchange: the caller's all-reduce (the barrier that ends the step)
+        s.timer.mark(s.stream);   // integrate: fused into the traversal
+        s.pcur = (s.pcur + 2) % 3;
+        s.vcur ^= 1;
+        s.maxabs_slot ^= 1;
+    }
+    s.step_pending = false;
+    s.tree_valid = false;
+    ++s.steps;
+    if (s.timer.enabled) {
+        B200_CHECK(cudaStreamSynchronize(s.stream));
+        s.timer.collect();
+    }
+}
+
 static void step_plain(NBodySim& s, double dt)
 {
     if (s.shard_begin == 0 && s.shard_end == s.n) {
@@ -1518,6 +1578,25 @@ __global__ void __launch_bounds__(256) frame_kernel(const double* __restrict__ p
     fcol[w] = r; fcol[w + 1] = g; fcol[w + 2] = b;
 }
 
+// rows [row_begin, row_end) of the frame only (sharded egress: a rank copies out 1 / world of the rows, so it
+// un-permutes only those: every thread reads the 4-byte creation index, one in `world` does the rest)
+__global__ void __launch_bounds__(256) frame_rows_kernel(const double* __restrict__ pos, const double* __restrict__ vel,
+                                                         const uint32_t* __restrict__ id, float* __restrict__ fpos,
+                                                         float* __restrict__ fcol, int n, double max_speed, uint32_t row_begin,
+                                                         uint32_t row_end)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t c = id[k];
+    if (c < row_begin || c >= row_end) return;
+    const int64_t o = 3 * (int64_t)k, w = 3 * (int64_t)c;
+    const double vx = vel[o], vy = vel[o + 1], vz = vel[o + 2];
+    float r, g, b;
+    speed_color(fmin(1.0, sqrt(vx * vx + vy * vy + vz * vz) / max_speed), r, g, b);
+    fpos[w] = (float)pos[o]; fpos[w + 1] = (float)pos[o + 1]; fpos[w + 2] = (float)pos[o + 2];
+    fcol[w] = r; fcol[w + 1] = g; fcol[w + 2] = b;
+}
+
 // ---------------------------------------------------------------------------- bucketed un-permute (large n)
 // frame_kernel's un-permute to creation order is a random 12-byte scatter: every store is a partial
 // sector, read-modify-written in DRAM (6.5 ms at 50 M).  For large n the frame is produced in three
@@ -1596,11 +1675,15 @@ __global__ void __launch_bounds__(256) unperm_scatter_kernel(const float4* __res
 }
 
 // colours + creation-order float32 positions of the current state into (fpos, fcol), on the handle's stream
-static void launch_frame(NBodySim& s, float* fpos, float* fcol, double max_speed)
+static void launch_frame(NBodySim& s, float* fpos, float* fcol, double max_speed, int row_begin = 0, int row_end = -1)
 {
     const int n = s.n;
     cudaStream_t st = s.stream;
-    if (n < s.unperm_min_n || !s.unperm_counts) {
+    if (row_end >= 0 && (row_begin > 0 || row_end < n) && 2 * (int64_t)(row_end - row_begin) <= n) {
+        frame_rows_kernel<<<div_up(n, 256), 256, 0, st>>>(s.pos[s.pcur], s.vel[s.vcur], s.id[s.vcur], fpos, fcol, n, max_speed,
+                                                          (uint32_t)row_begin, (uint32_t)row_end);
+        ++s.launches;
+    } else if (n < s.unperm_min_n || !s.unperm_counts) {
         frame_kernel<<<div_up(n, 256), 256, 0, st>>>(s.pos[s.pcur], s.vel[s.vcur], s.id[s.vcur], fpos, fcol, n, max_speed);
         ++s.launches;
     } else {
@@ -1633,7 +1716,8 @@ void nbody_frame_begin_rows(NBodySim& s, double max_speed, float* host_pos, floa
     if (s.n == 0) return;
     async_init(s);
     if (s.frame_pending) B200_CHECK(cudaStreamWaitEvent(s.stream, s.ev_frame_done, 0));   // staging still being read
-    launch_frame(s, s.frame_pos, s.frame_col, max_speed);
+    launch_frame(s, s.frame_pos, s.frame_col, max_speed, row_begin, row_end);
+    const bool partial_frame = row_begin > 0 || row_end < s.n;   // (a partial frame cannot seed a delta frame)
     B200_CHECK(cudaEventRecord(s.ev_frame_ready, s.stream));
     B200_CHECK(cudaStreamWaitEvent(s.down_stream, s.ev_frame_ready, 0));
     const size_t off = 3 * (size_t)row_begin, bytes = 3 * (size_t)(row_end - row_begin) * sizeof(float);
@@ -1644,7 +1728,7 @@ void nbody_frame_begin_rows(NBodySim& s, double max_speed, float* host_pos, floa
     B200_CHECK(cudaMemcpyAsync(s.h_error, s.d_error, sizeof(unsigned), cudaMemcpyDeviceToHost, s.down_stream));
     B200_CHECK(cudaEventRecord(s.ev_frame_done, s.down_stream));
     s.frame_pending = true;
-    s.frame_has_prev = true;
+    s.frame_has_prev = !partial_frame;
 }
 
 // ---------------------------------------------------------------------------- delta frames (frame codec)

@@ -22,6 +22,7 @@
 #pragma once
 #include "common.cuh"
 #include "radix_sort.cuh"
+#include <vector>
 
 namespace b200 {
 
@@ -161,6 +162,29 @@ void nbody_graphs_reset(NBodySim& s);
 void nbody_step_begin(NBodySim& s);
 void nbody_step_begin_sorted(NBodySim& s);   // after nbody_ms_sort_local + the all-gather of the exchange buffers
 void nbody_step_end(NBodySim& s, double dt);
+// ---- sharded fused step (multi-GPU inside the library, see multi.cu): every rank holds the full replicated
+// state, sorts one slice, builds the whole tree, traverses and integrates only its shard, and its traversal
+// kernel writes the new positions / velocities of those bodies into the next-state buffers of EVERY rank
+// (peer-mapped memory over NVLink).  The caller supplies the collectives between the pieces.
+constexpr int SHARD_MAX_WORLD = 8;
+struct ShardPeers {                            // next-state buffers of every rank, as seen from this device
+    double* pos[SHARD_MAX_WORLD][3];
+    double* vel[SHARD_MAX_WORLD][2];
+    int world = 1;
+};
+void nbody_shard_build(NBodySim& s, bool presorted);   // (merge of the all-gathered runs +) gather, tree, records
+void nbody_shard_traverse(NBodySim& s, double dt, const ShardPeers& peers);   // forces + integration + broadcast of the shard
+void nbody_shard_finish(NBodySim& s);          // host side: advance the state buffers (after the caller's all-reduce of d_maxabs)
+unsigned long long* nbody_shard_maxabs_next(NBodySim& s);
+// multi.cu
+struct NBodyGroup;
+void nccl_unique_id(void* out128);
+NBodyGroup* group_create_rank(NBodySim& s, const void* id128, int rank, int world);
+NBodyGroup* group_create_local(const std::vector<NBodySim*>& sims);
+void group_destroy(NBodyGroup* g);
+int group_world(const NBodyGroup* g);
+void group_state_replaced(NBodyGroup* g);
+void group_step(NBodyGroup& g, double dt);
 double fp32_peak_tflops(int device);
 void nbody_compute_colors(NBodySim& s, double max_speed);
 // after a synchronisation: throws StateError if a kernel raised a device error flag (sticky)

@@ -100,6 +100,7 @@ __device__ __forceinline__ void finish_body(const StepOut& o, int k, float ax, f
 
 __device__ __forceinline__ void finish_warp(const StepOut& o, double m)
 {
+    if (o.world > 1) __threadfence_system();   // the stores into the peers' buffers are performed before the kernel ends
     for (int s = 16; s > 0; s >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, s));
     if (lane_id() == 0) atomicMax(o.maxabs, (unsigned long long)__double_as_longlong(m));
 }

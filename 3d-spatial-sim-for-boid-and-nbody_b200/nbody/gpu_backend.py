@@ -89,7 +89,10 @@ class B200BarnesHutSimulation:
     """Device-resident Barnes-Hut simulation (duck type of CUDASimulation, gpu_backend.py:336-409)."""
 
     def __init__(self, positions: np.ndarray, velocities: np.ndarray, masses: np.ndarray,
-                 G: float, softening: float, damping: float, theta: float = 0.5, device: int = 0):
+                 G: float, softening: float, damping: float, theta: float = 0.5, device: int = 0,
+                 device_mask: Optional[int] = None):
+        """device_mask (bit d = CUDA device d): one handle driving several GPUs of this process (the sharded
+        step with NCCL + peer-to-peer stores inside the library); default: the single `device`."""
         L = _lib.load()
         pos = _as_f64(positions, (3,))
         vel = _as_f64(velocities, (3,))
@@ -105,9 +108,17 @@ class B200BarnesHutSimulation:
         self._L = L
         self._h = C.c_void_p()
         dp = C.POINTER(C.c_double)
-        _lib.check(L.b200_nbody_create(self.n, pos.ctypes.data_as(dp), vel.ctypes.data_as(dp),
-                                       mass.ctypes.data_as(dp), self.G, self.softening, self.damping,
-                                       self.theta, self.device, C.byref(self._h)))
+        if device_mask is None or device_mask == (1 << self.device):
+            _lib.check(L.b200_nbody_create(self.n, pos.ctypes.data_as(dp), vel.ctypes.data_as(dp),
+                                           mass.ctypes.data_as(dp), self.G, self.softening, self.damping,
+                                           self.theta, self.device, C.byref(self._h)))
+        else:
+            mask = int(device_mask)
+            self.device = (mask & -mask).bit_length() - 1      # getters are served by the lowest device
+            _lib.check(L.b200_nbody_create_multi(self.n, pos.ctypes.data_as(dp), vel.ctypes.data_as(dp),
+                                                 mass.ctypes.data_as(dp), self.G, self.softening, self.damping,
+                                                 self.theta, mask, C.byref(self._h)))
+            print(f"[CUDA] {bin(mask).count('1')} GPUs (device mask {mask:#x}): Morton-range shards, NCCL + NVLink peer stores")
         print(f"[CUDA] Initialized with {self.n:,} bodies")
         print(f"[CUDA] Using B200 Barnes-Hut kernel (theta={self.theta})")
 
@@ -278,7 +289,24 @@ class B200BarnesHutSimulation:
         _lib.check(self._L.b200_nbody_launch_count(self._handle(), C.byref(v)))
         return int(v.value)
 
-    # sharded step pieces (see b200sim.nbody.sharded for the torch.distributed plumbing)
+    # one process per GPU: join the ranks into one sharded simulation (collective; see include/b200sim.h)
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.load().b200_nccl_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be the 128 bytes of b200_nccl_unique_id")
+        _lib.check(self._L.b200_nbody_comm_init(self._handle(), C.c_char_p(unique_id), int(rank), int(world)))
+
+    def world(self) -> int:
+        w = C.c_int(1)
+        _lib.check(self._L.b200_nbody_world(self._handle(), C.byref(w)))
+        return int(w.value)
+
+    # split sharded step pieces (building blocks; tests compose them on one device)
     def set_stream(self, cuda_stream):
         """Run all device work on the given cudaStream_t (int; 0 = legacy default stream);
         None returns to the handle's own stream."""
@@ -376,6 +404,11 @@ def create_gpu_simulation(positions: np.ndarray, velocities: np.ndarray, masses:
     n = len(positions)
     if backend == Backend.CUDA:
         if n <= CUDA_THRESHOLD or force_gpu:
-            return B200BarnesHutSimulation(positions, velocities, masses, G, softening, damping, theta)
+            # B200SIM_DEVICE_MASK (e.g. 0xff): the reference's callers have no device argument; the environment
+            # variable lets tools.record drive several GPUs through this unchanged factory
+            import os
+            mask = os.environ.get("B200SIM_DEVICE_MASK")
+            return B200BarnesHutSimulation(positions, velocities, masses, G, softening, damping, theta,
+                                           device_mask=int(mask, 0) if mask else None)
         return None
     return None  # CPU: the caller's own Barnes-Hut path (the reference's, not this package's)

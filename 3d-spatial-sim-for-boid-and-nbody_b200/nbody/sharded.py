@@ -1,13 +1,16 @@
 """Morton-range sharding of the Barnes-Hut step over the GPUs of one box.
 
-One process per GPU (torchrun); ``torch.distributed`` (NCCL over NVLink/NVSwitch) is the
-plumbing.  Every rank holds the full replicated fp64 state, sorts and builds the whole tree
-(redundant, cheap), traverses only its contiguous slice of the Morton-sorted bodies, then one
-all-gather of the accelerations (16 B/body) makes every rank's buffer complete and every rank
-integrates all bodies.  Integration is elementwise and the sort is deterministic, so the
-replicas stay bit-identical without exchanging positions, velocities or tree data.
+The sharded step itself lives in the library (csrc/multi.cu, include/b200sim.h "several GPUs behind the C
+ABI"): every rank holds the full replicated fp64 state, radix-sorts one slice of it (NCCL all-gather of the
+sorted runs, merge by counting), builds the whole tree (deterministic, so identical everywhere), and traverses
+and integrates only its contiguous Morton range; the traversal kernel stores the new positions and velocities
+of those bodies straight into the next-state buffers of every rank over NVLink peer mappings, and an 8-byte
+all-reduce ends the step.  Replicas stay bit-identical to each other and to a single-GPU run.
 
-The reference has no multi-GPU code; this is new design.
+This module is the one-process-per-GPU (torchrun) front end: ``torch.distributed`` carries the 128-byte NCCL
+id to the ranks and provides the stream the library works on; the collectives of the step are issued by the
+library.  (One process driving several GPUs needs no torch at all: ``B200BarnesHutSimulation(...,
+device_mask=0xff)``.)  The reference has no multi-GPU code; this is new design.
 """
 from __future__ import annotations
 
@@ -44,6 +47,18 @@ def all_gather_slices(buf, rank: int, world: int, group=None):
     return buf
 
 
+def broadcast_unique_id(rank: int, group=None) -> bytes:
+    """Rank 0 draws the NCCL id through the library, torch.distributed carries it to the others."""
+    import torch
+    import torch.distributed as dist
+    from .gpu_backend import B200BarnesHutSimulation
+    uid = B200BarnesHutSimulation.nccl_unique_id() if rank == 0 else bytes(128)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor(list(uid), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0, group=group)
+    return bytes(t.cpu().tolist())
+
+
 class _DeviceArray:
     """Minimal __cuda_array_interface__ carrier so torch can view library-owned memory."""
 
@@ -53,60 +68,32 @@ class _DeviceArray:
 
 
 class ShardedSimulation:
-    """Wraps a B200BarnesHutSimulation replica on this rank's GPU; same duck type
-    (step / compute_colors / get_* / sync) as the single-GPU object."""
+    """Rank `rank` of `world` (one process per GPU): wraps this rank's B200BarnesHutSimulation replica; same
+    duck type (step / compute_colors / get_* / sync) as the single-GPU object.  Every call that changes the
+    state must be made by all ranks alike."""
 
-    def __init__(self, sim, rank: int, world: int, group=None, sharded_sort: bool = True):
+    def __init__(self, sim, rank: int, world: int, group=None):
         import torch
         self.sim, self.rank, self.world, self.group = sim, rank, world, group
         self.n = sim.n
         self.S = slice_size(sim.n, world)
-        begin, end = partition_equal(sim.n, world)[rank]
-        sim.set_shard(begin, end)
-        ptr, cap = sim.acc_buffer()
-        if cap < self.S * world:
-            raise RuntimeError("accelerations buffer too small for the padded slices")
         self._torch = torch
         dev = torch.device("cuda", sim.device)
-        self.acc_all = torch.as_tensor(_DeviceArray(ptr, (self.S * world, 4)), device=dev)
-        # all library work on torch's current stream: the collective is ordered with the kernels
+        # all library work (kernels and the library's own NCCL calls) on torch's current stream
         sim.set_stream(torch.cuda.current_stream(dev).cuda_stream)
-        # sharded sort: every rank sorts one slice of the (Morton-ordered) state, the sorted slices are
-        # all-gathered (12 B/body) and merged by counting on every rank.  Only once the state is in Morton
-        # order (from the second step after an upload); the first step sorts everything on every rank.
-        self.sharded_sort = sharded_sort and world > 1
-        self._in_morton_order = False
         self._stage = None
-        if self.sharded_sort:
-            kp, vp = sim.sharded_sort_setup(self.S, world)
-            self.keys_all = torch.as_tensor(_DeviceArray(kp, (self.S * world, 1), "<i8"), device=dev)
-            self.vals_all = torch.as_tensor(_DeviceArray(vp, (self.S * world, 1), "<i4"), device=dev)
+        if world > 1:
+            sim.comm_init(broadcast_unique_id(rank, group), rank, world)
 
     def step(self, dt: float):
-        if self.world == 1:      # nothing to exchange: the library's captured step (CUDA graph)
-            self.sim.step(dt)
-            self._in_morton_order = True
-            return
-        if self.sharded_sort and self._in_morton_order:
-            self.sim.sort_local(self.rank)
-            all_gather_slices(self.keys_all, self.rank, self.world, self.group)
-            all_gather_slices(self.vals_all, self.rank, self.world, self.group)
-            self.sim.step_begin_sorted()
-        else:
-            self.sim.step_begin()
-        if self.world > 1:
-            all_gather_slices(self.acc_all, self.rank, self.world, self.group)
-        self.sim.step_end(dt)
-        self._in_morton_order = True
+        self.sim.step(dt)            # world > 1: the sharded fused step inside the library
 
     def shard_bodies(self) -> int:
-        """Bodies this rank traverses (and sorts, with the sharded sort)."""
+        """Bodies this rank sorts, traverses and integrates."""
         b, e = partition_equal(self.n, self.world)[self.rank]
         return e - b
 
-    # a new state arrives in creation order: the next step must sort everything
     def set_state(self, positions, velocities):
-        self._in_morton_order = False
         self.sim.set_state(positions, velocities)
 
     # sharded host traffic: every rank moves 1/world of the rows over its own PCIe link; the upload is
@@ -119,7 +106,6 @@ class ShardedSimulation:
         self.sim.set_state_begin(positions, velocities, rows=self.host_rows() if self.world > 1 else None)
 
     def set_state_commit(self):
-        self._in_morton_order = False
         if self.world > 1:
             torch = self._torch
             if self._stage is None:

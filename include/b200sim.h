@@ -134,7 +134,29 @@ int b200_nbody_timed_steps(b200_nbody* h, double dt, int nsteps, float* elapsed_
 /* Kernels launched by this handle so far (bench.py's gpu_launches). */
 int b200_nbody_launch_count(b200_nbody* h, int64_t* out);
 
-/* ---- sharded (multi-GPU) step ------------------------------------------------------------
+/* ---- several GPUs behind the C ABI -------------------------------------------------------------
+ * The sharded step lives inside the library (csrc/multi.cu): every rank holds the full replicated state,
+ * radix-sorts one slice of it (the sorted runs are all-gathered with NCCL, loaded at run time, and merged by
+ * counting), builds the whole tree, and traverses + integrates only its own Morton range; the traversal
+ * kernel stores the new positions and velocities of those bodies straight into the next-state buffers of
+ * every rank over NVLink peer mappings, and one 8-byte all-reduce (the next bounds) is the barrier that ends
+ * the step.  Replicas stay bit-identical to each other and to a single-GPU run.  At most 8 ranks.
+ *
+ * (a) one process, several GPUs -- SURVEY.md 8b's `device_mask`: bit d of the mask selects CUDA device d.  The
+ *     handle behaves like a single-GPU one (getters and frames are served by the lowest device); this is how
+ *     a caller without torch, e.g. the reference's recorder through create_gpu_simulation, uses N GPUs. */
+int b200_nbody_create_multi(int64_t n, const double* pos, const double* vel, const double* mass,
+                            double G, double softening, double damping, double theta,
+                            uint32_t device_mask, b200_nbody** out);
+/* (b) one process per GPU (torchrun): rank 0 draws 128 bytes (an ncclUniqueId), the caller carries them to
+ *     every rank by any means, and every rank calls comm_init on its own handle (collective).  The other
+ *     ranks' state buffers are mapped with CUDA IPC.  From then on step() is the sharded step, and every call
+ *     that changes the state (step, set_state, compute_accelerations, ...) must be made by all ranks alike. */
+int b200_nccl_unique_id(void* out128);
+int b200_nbody_comm_init(b200_nbody* h, const void* id128, int rank, int world);
+int b200_nbody_world(b200_nbody* h, int* world);
+
+/* ---- split sharded step (building blocks; the collectives are the caller's) -------------------
  * One process per GPU, every rank holds the full replicated state and builds the full tree;
  * a rank traverses only sorted bodies [begin, end) (begin a multiple of 32).  Between
  * step_begin and step_end the host-side plumbing (torch.distributed / NCCL) all-gathers the

@@ -544,3 +544,17 @@ def test_multi_gpu_replicas_match_unsharded_twin():
            "--master-port", "29533", os.path.join(root, "scripts", "mgpu_check.py"), "60001"]
     res = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "MGPU CHECK PASSED" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_device_mask_handle_matches_single_gpu_twin():
+    """One process, several GPUs through the C ABI alone (b200_nbody_create_multi): NCCL inside the library,
+    new positions stored into the peers' buffers by the traversal kernel.  Needs two GPUs on the box."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "scripts", "mgpu_mask_check.py"), "60001", "0x3"], cwd=root,
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "MASK CHECK PASSED" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
