@@ -62,6 +62,9 @@ SIGNATURES = {
                                     C.c_int, C.POINTER(_h)]),
     "b200_nbody_create_multi": (C.c_int, [C.c_int64, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double,
                                           C.c_uint32, C.POINTER(_h)]),
+    "b200_generate_distribution": (C.c_int, [C.c_char_p, C.c_int64, C.c_double, C.c_double, C.c_uint64, C.c_int, _dp, _dp, _dp]),
+    "b200_nbody_create_generated": (C.c_int, [C.c_char_p, C.c_int64, C.c_double, C.c_double, C.c_uint64, C.c_double, C.c_double,
+                                              C.c_double, C.c_double, C.c_int, C.POINTER(_h)]),
     "b200_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "b200_nbody_comm_init": (C.c_int, [_h, C.c_void_p, C.c_int, C.c_int]),
     "b200_nbody_world": (C.c_int, [_h, C.POINTER(C.c_int)]),

@@ -11,7 +11,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libb200sim.so")
-SOURCES = ["nbody.cu", "multi.cu", "boids.cu", "capi.cu"]
+SOURCES = ["nbody.cu", "multi.cu", "boids.cu", "generate.cu", "capi.cu"]
 HEADERS = ["common.cuh", "radix_sort.cuh", "nbody.cuh", "traverse.cuh", "boids.cuh",
            os.path.join("..", "..", "include", "b200sim.h")]
 

@@ -111,6 +111,59 @@ B200_API int b200_nbody_create(int64_t n, const double* pos, const double* vel, 
     return B200_OK;
 }
 
+B200_API int b200_generate_distribution(const char* distribution, int64_t n, double R, double G, uint64_t seed, int device,
+                                        double* pos, double* vel, double* mass)
+{
+    B200_ARG(distribution, "distribution name is null");
+    B200_ARG(n >= 0 && n < (int64_t)1 << 30, "n out of range [0, 2^30)");
+    B200_ARG(n == 0 || (pos && vel && mass), "pos/vel/mass is null");
+    B200_TRY({
+        B200_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        B200_CHECK(cudaGetDeviceProperties(&prop, device));
+        const size_t N = (size_t)n;
+        double* d = b200::dev_alloc<double>(7 * N);
+        try {
+            b200::generate_device(b200::generator_id(distribution), n, R, G, seed, d, d + 3 * N, d + 6 * N, nullptr,
+                                  prop.multiProcessorCount);
+            B200_CHECK(cudaMemcpy(pos, d, 3 * N * sizeof(double), cudaMemcpyDeviceToHost));
+            B200_CHECK(cudaMemcpy(vel, d + 3 * N, 3 * N * sizeof(double), cudaMemcpyDeviceToHost));
+            B200_CHECK(cudaMemcpy(mass, d + 6 * N, N * sizeof(double), cudaMemcpyDeviceToHost));
+        } catch (...) {
+            cudaFree(d);
+            throw;
+        }
+        cudaFree(d);
+    })
+}
+
+B200_API int b200_nbody_create_generated(const char* distribution, int64_t n, double R, double G_dist, uint64_t seed,
+                                         double G, double softening, double damping, double theta, int device, b200_nbody** out)
+{
+    B200_ARG(out, "out handle is null");
+    *out = nullptr;
+    B200_ARG(distribution, "distribution name is null");
+    B200_ARG(n >= 0 && n < (int64_t)1 << 30, "n out of range [0, 2^30)");
+    B200_ARG(theta >= 0.0, "theta must be >= 0");
+    b200_nbody* h = new b200_nbody();
+    try {
+        h->sim.device = device;
+        h->sim.G = G;
+        h->sim.softening = softening;
+        h->sim.damping = damping;
+        h->sim.theta = theta;
+        b200::nbody_alloc(h->sim, (int)n);
+        b200::nbody_generate(h->sim, b200::generator_id(distribution), R, G_dist, seed);
+    } catch (const b200::CudaError& e) {
+        b200::set_error(e.msg);
+        b200::nbody_free(h->sim);
+        delete h;
+        return B200_ERR_CUDA;
+    }
+    *out = h;
+    return B200_OK;
+}
+
 B200_API int b200_nbody_destroy(b200_nbody* h)
 {
     if (!h) return B200_OK;

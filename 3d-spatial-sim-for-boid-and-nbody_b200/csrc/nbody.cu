@@ -802,6 +802,20 @@ void nbody_upload(NBodySim& s, const double* pos, const double* vel, const doubl
     B200_CHECK(cudaStreamSynchronize(s.stream));
 }
 
+// Initial state drawn on the device, straight into the state buffers (generate.cu).
+void nbody_generate(NBodySim& s, int dist, double R, double G_dist, uint64_t seed)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    s.pcur = 0;
+    s.vcur = 0;
+    generate_device(dist, s.n, R, G_dist, seed, s.pos[0], s.vel[0], s.mass[0], s.stream, s.sm_count);
+    B200_CHECK(cudaMemcpyAsync(s.mass0, s.mass[0], (size_t)s.n * sizeof(double), cudaMemcpyDeviceToDevice, s.stream));
+    if (s.n > 0) iota_kernel<<<div_up(s.n, 256), 256, 0, s.stream>>>(s.id[0], s.n);
+    recompute_maxabs(s);
+    s.tree_valid = false;
+    B200_CHECK(cudaStreamSynchronize(s.stream));
+}
+
 // New positions / velocities for the same bodies, given in creation order.
 void nbody_upload_state(NBodySim& s, const double* pos, const double* vel)
 {

@@ -145,6 +145,12 @@ void nbody_alloc(NBodySim& s, int n);
 void nbody_free(NBodySim& s);
 void nbody_upload(NBodySim& s, const double* pos, const double* vel, const double* mass);
 void nbody_upload_state(NBodySim& s, const double* pos, const double* vel);
+// generate.cu: seeded initial conditions on the device (tools/presets.py:91-1390, generate_distribution)
+int generator_id(const char* name);
+void generate_device(int dist, int64_t n, double R, double G, uint64_t seed, double* pos, double* vel, double* mass,
+                     cudaStream_t stream, int sm_count);
+// initial state of the handle generated in place (no host traffic)
+void nbody_generate(NBodySim& s, int dist, double R, double G_dist, uint64_t seed);
 // keygen .. extract: leaves keys/perm/tree valid for the current positions; the state is physically in the new
 // Morton order afterwards (positions, velocities, masses, ids)
 void nbody_build_tree(NBodySim& s);

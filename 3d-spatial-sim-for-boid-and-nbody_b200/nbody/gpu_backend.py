@@ -122,6 +122,25 @@ class B200BarnesHutSimulation:
         print(f"[CUDA] Initialized with {self.n:,} bodies")
         print(f"[CUDA] Using B200 Barnes-Hut kernel (theta={self.theta})")
 
+    @classmethod
+    def from_distribution(cls, distribution: str, n: int, R: float, G_dist: float, G: float, softening: float,
+                          damping: float, theta: float = 0.5, seed: int = 0, device: int = 0):
+        """generate_distribution(distribution, n, R, G_dist) (tools/presets.py:91) + create_gpu_simulation in one
+        call, with the initial state drawn on the device straight into the handle's buffers (csrc/generate.cu):
+        no host arrays, no upload (50 M bodies in a fraction of a second)."""
+        self = cls.__new__(cls)
+        L = _lib.load()
+        self.n, self.G, self.softening, self.damping, self.theta = int(n), float(G), float(softening), float(damping), float(theta)
+        self.device = int(device)
+        self._L = L
+        self._h = C.c_void_p()
+        _lib.check(L.b200_nbody_create_generated(str(distribution).encode(), self.n, float(R), float(G_dist), int(seed),
+                                                 self.G, self.softening, self.damping, self.theta, self.device,
+                                                 C.byref(self._h)))
+        print(f"[CUDA] Initialized with {self.n:,} bodies")
+        print(f"[CUDA] Using B200 Barnes-Hut kernel (theta={self.theta})")
+        return self
+
     # ---- reference duck type -------------------------------------------------------------
     def step(self, dt: float):
         """One force evaluation + kick-drift (gpu_backend.py:368-386; semantics of

@@ -123,6 +123,29 @@ def generate(distribution: str, n: int, R: float, G: float, seed: int = 0):
     return np.ascontiguousarray(pos), np.ascontiguousarray(vel), mass
 
 
+DISTRIBUTIONS = (
+    "galaxy", "collision", "spiral", "sphere", "ring", "shell", "cluster", "binary", "elliptical", "bar", "stream",
+    "filament", "explosion", "disc", "vortex", "cube", "pleiades", "double_helix", "accretion_disk", "torus",
+    "hourglass", "fibonacci", "triple", "rosette", "dyson")   # tools/presets.py:23-49
+
+
+def generate_distribution(distribution: str, n: int, R: float, G: float, seed: int = 0, device: int = 0):
+    """Drop-in for the reference's generate_distribution(distribution, n, R, G) (tools/presets.py:91-1390): all
+    25 laws, generated ON THE GPU by libb200sim.so (csrc/generate.cu) from a seed -- reproducible, one thread
+    per body, no per-body Python loops -- and copied back as the reference's three host arrays
+    positions (n,3), velocities (n,3), masses (n) [fp64].  An unknown name gives the sphere, like the
+    reference's final else.  Raises if the library or a GPU is missing (no CPU fallback);
+    B200BarnesHutSimulation.from_distribution keeps the state on the device instead."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.load()
+    pos, vel, mass = np.empty((n, 3)), np.empty((n, 3)), np.empty(n)
+    dp = C.POINTER(C.c_double)
+    _lib.check(L.b200_generate_distribution(str(distribution).encode(), int(n), float(R), float(G), int(seed), int(device),
+                                            pos.ctypes.data_as(dp), vel.ctypes.data_as(dp), mass.ctypes.data_as(dp)))
+    return pos, vel, mass
+
+
 def generate_preset(key: str, seed: int = 0, num_bodies: int | None = None):
     cfg = get_preset_config(key)
     n = cfg["num_bodies"] if num_bodies is None else int(num_bodies)

@@ -69,6 +69,17 @@ int b200_nbody_create(int64_t n, const double* pos, const double* vel, const dou
                       double G, double softening, double damping, double theta,
                       int device, b200_nbody** out);
 int b200_nbody_destroy(b200_nbody* h);
+/* Seeded initial conditions generated ON THE DEVICE: replaces generate_distribution(distribution,
+ * n, R, G) of tools/presets.py:91-1390 (the 25 laws of tools/presets.py:23-49; an unknown name gives the sphere,
+ * like the reference's final else).  Body i is drawn from Philox4x32-10 with counter (i, draw, stream, 0) and
+ * key = seed: reproducible, independent of n, no per-body host loops.  Host outputs: pos (n,3), vel (n,3),
+ * mass (n), fp64. */
+int b200_generate_distribution(const char* distribution, int64_t n, double R, double G, uint64_t seed, int device,
+                               double* pos, double* vel, double* mass);
+/* create() with the initial state drawn straight into the handle's device buffers (no host arrays, no upload):
+ * generate_distribution(distribution, n, R, G_dist) followed by create(..., G, softening, damping, theta). */
+int b200_nbody_create_generated(const char* distribution, int64_t n, double R, double G_dist, uint64_t seed,
+                                double G, double softening, double damping, double theta, int device, b200_nbody** out);
 /* step: replaces CUDASimulation.step (nbody/gpu_backend.py:368-386): one force evaluation +
  * kick-drift.  Asynchronous with respect to the host. */
 int b200_nbody_step(b200_nbody* h, double dt);
