@@ -93,6 +93,8 @@ SIGNATURES = {
     "b200_nbody_frame_begin": (C.c_int, [_h, C.c_double, _fp, _fp]),
     "b200_nbody_frame_wait": (C.c_int, [_h]),
     "b200_nbody_frame_delta_begin": (C.c_int, [_h, C.c_double, C.POINTER(C.c_int16), C.POINTER(C.c_int16)]),
+    "b200_nbody_visible_frame": (C.c_int, [_h, C.c_double, _dp, _fp, _fp, C.POINTER(C.c_int64)]),
+    "b200_nbody_visible_frame_device": (C.c_int, [_h, C.c_double, _dp, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "b200_nbody_set_state_begin": (C.c_int, [_h, _dp, _dp]),
     "b200_nbody_set_state_commit": (C.c_int, [_h]),
     "b200_nbody_set_state_begin_rows": (C.c_int, [_h, _dp, _dp, C.c_int64, C.c_int64]),

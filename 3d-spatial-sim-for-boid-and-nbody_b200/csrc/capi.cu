@@ -240,6 +240,29 @@ B200_API int b200_nbody_create_multi(int64_t n, const double* pos, const double*
     return B200_OK;
 }
 
+static int visible_frame(b200_nbody* h, double max_speed, const double* camera, float* pos, float* col, int64_t* count, bool to_device)
+{
+    B200_ARG(h && camera && count, "null argument");
+    B200_ARG(h->sim.n == 0 || (pos && col), "output buffer is null");
+    B200_TRY({
+        b200::Camera c;
+        for (int k = 0; k < 3; ++k) { c.pos[k] = camera[k]; c.forward[k] = camera[3 + k]; c.right[k] = camera[6 + k]; c.up[k] = camera[9 + k]; }
+        c.tan_h = camera[12]; c.tan_v = camera[13]; c.far_dist = camera[14];
+        *count = b200::nbody_visible_frame(h->sim, max_speed, c, pos, col, to_device);
+    })
+}
+
+B200_API int b200_nbody_visible_frame(b200_nbody* h, double max_speed, const double* camera, float* pos_out, float* col_out, int64_t* count)
+{
+    return visible_frame(h, max_speed, camera, pos_out, col_out, count, false);
+}
+
+B200_API int b200_nbody_visible_frame_device(b200_nbody* h, double max_speed, const double* camera, void* pos_device, void* col_device,
+                                            int64_t* count)
+{
+    return visible_frame(h, max_speed, camera, (float*)pos_device, (float*)col_device, count, true);
+}
+
 B200_API int b200_nbody_step(b200_nbody* h, double dt)
 {
     B200_ARG(h, "handle is null");

@@ -766,6 +766,8 @@ void nbody_free(NBodySim& s)
     cudaFree(s.d_error);
     if (s.h_error) { cudaFreeHost(s.h_error); s.h_error = nullptr; }
     s.timer.destroy();
+    if (s.vis_counts) { cudaFree(s.vis_counts); cudaFreeHost(s.vis_total_host); s.vis_counts = nullptr; s.vis_total_host = nullptr; }
+    if (s.vis_pos) { cudaFree(s.vis_pos); cudaFree(s.vis_col); s.vis_pos = s.vis_col = nullptr; }
     async_free(s);
     if (s.own_stream) cudaStreamDestroy(s.own_stream);
     s.own_stream = nullptr;
@@ -1812,6 +1814,149 @@ void nbody_frame_delta_begin(NBodySim& s, double max_speed, short* host_dpos, sh
     B200_CHECK(cudaMemcpyAsync(s.h_error, s.d_error, sizeof(unsigned), cudaMemcpyDeviceToHost, s.down_stream));
     B200_CHECK(cudaEventRecord(s.ev_frame_done, s.down_stream));
     s.frame_pending = true;
+}
+
+// ---------------------------------------------------------------------------- live-viewer path
+// The reference's viewer copies every position and colour to the host each frame (nbody/simulation.py:809-817),
+// tests all of them against the view frustum on the CPU (compute_visibility_points, :403-434), gathers the visible
+// ones with a boolean mask (:926-927) and uploads those to two VBOs.  Here the test and the gather run on the
+// device over the creation-order fp32 frame (the reference tests float32 positions widened to float64: :816), and
+// only the visible bodies leave the GPU -- or none do, when the caller passes a mapped VBO.
+constexpr int VIS_ITEMS = 4;
+constexpr int VIS_TILE = 256 * VIS_ITEMS;
+
+__device__ __forceinline__ bool frustum_visible(const float* __restrict__ fpos, int64_t i, const Camera& c)
+{
+    // the arithmetic of compute_visibility_points, operation by operation, without contraction
+    const double dx = __dsub_rn((double)fpos[3 * i], c.pos[0]), dy = __dsub_rn((double)fpos[3 * i + 1], c.pos[1]),
+                 dz = __dsub_rn((double)fpos[3 * i + 2], c.pos[2]);
+    const double z = __dadd_rn(__dadd_rn(__dmul_rn(dx, c.forward[0]), __dmul_rn(dy, c.forward[1])), __dmul_rn(dz, c.forward[2]));
+    if (z < 0.1 || z > c.far_dist) return false;
+    const double x = __dadd_rn(__dadd_rn(__dmul_rn(dx, c.right[0]), __dmul_rn(dy, c.right[1])), __dmul_rn(dz, c.right[2]));
+    const double y = __dadd_rn(__dadd_rn(__dmul_rn(dx, c.up[0]), __dmul_rn(dy, c.up[1])), __dmul_rn(dz, c.up[2]));
+    const double hw = __dmul_rn(__dmul_rn(z, c.tan_h), 1.2), hh = __dmul_rn(__dmul_rn(z, c.tan_v), 1.2);
+    return fabs(x) < hw && fabs(y) < hh;
+}
+
+__global__ void __launch_bounds__(256) vis_count_kernel(const float* __restrict__ fpos, int n, Camera cam, unsigned* __restrict__ counts)
+{
+    const int64_t base = (int64_t)blockIdx.x * VIS_TILE + (int64_t)threadIdx.x * VIS_ITEMS;
+    int c = 0;
+#pragma unroll
+    for (int q = 0; q < VIS_ITEMS; ++q)
+        if (base + q < n && frustum_visible(fpos, base + q, cam)) ++c;
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ int sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        counts[blockIdx.x] = (unsigned)t;
+    }
+}
+
+// exclusive scan of the block counts in place (one CTA; the total lands in counts[blocks])
+__global__ void __launch_bounds__(1024) vis_scan_kernel(unsigned* __restrict__ counts, int blocks)
+{
+    __shared__ unsigned sh[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0u;
+    __syncthreads();
+    for (int b0 = 0; b0 < blocks; b0 += 1024) {
+        const int i = b0 + (int)threadIdx.x;
+        const unsigned v = i < blocks ? counts[i] : 0u;
+        unsigned inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)(threadIdx.x & 31) >= o) inc += u;
+        }
+        if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned w = sh[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned u = __shfl_up_sync(0xffffffffu, w, o);
+                if ((int)threadIdx.x >= o) w += u;
+            }
+            sh[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const unsigned before = carry + (threadIdx.x >= 32 ? sh[(threadIdx.x >> 5) - 1] : 0u) + inc - v;
+        if (i < blocks) counts[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[blocks] = carry;
+}
+
+__global__ void __launch_bounds__(256) vis_compact_kernel(const float* __restrict__ fpos, const float* __restrict__ fcol, int n, Camera cam,
+                                                          const unsigned* __restrict__ offsets, float* __restrict__ out_pos,
+                                                          float* __restrict__ out_col)
+{
+    const int64_t base = (int64_t)blockIdx.x * VIS_TILE + (int64_t)threadIdx.x * VIS_ITEMS;
+    bool vis[VIS_ITEMS];
+    int c = 0;
+#pragma unroll
+    for (int q = 0; q < VIS_ITEMS; ++q) {
+        vis[q] = base + q < n && frustum_visible(fpos, base + q, cam);
+        c += vis[q];
+    }
+    int inc = c;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)(threadIdx.x & 31) >= o) inc += u;
+    }
+    __shared__ int sh[8];
+    if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    int before = inc - c;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += sh[w];
+    int64_t o = (int64_t)offsets[blockIdx.x] + before;
+#pragma unroll
+    for (int q = 0; q < VIS_ITEMS; ++q)
+        if (vis[q]) {
+            const int64_t i = base + q;
+            out_pos[3 * o] = fpos[3 * i]; out_pos[3 * o + 1] = fpos[3 * i + 1]; out_pos[3 * o + 2] = fpos[3 * i + 2];
+            out_col[3 * o] = fcol[3 * i]; out_col[3 * o + 1] = fcol[3 * i + 1]; out_col[3 * o + 2] = fcol[3 * i + 2];
+            ++o;
+        }
+}
+
+int64_t nbody_visible_frame(NBodySim& s, double max_speed, const Camera& cam, float* out_pos, float* out_col, bool to_device)
+{
+    B200_CHECK(cudaSetDevice(s.device));
+    if (s.n == 0) return 0;
+    async_init(s);
+    const int blocks = div_up(s.n, VIS_TILE);
+    if (!s.vis_counts) {
+        s.vis_counts = alloc_counted<unsigned>(s, (size_t)blocks + 1);
+        B200_CHECK(cudaMallocHost(&s.vis_total_host, sizeof(unsigned)));
+    }
+    if (!to_device && !s.vis_pos) {
+        s.vis_pos = alloc_counted<float>(s, 3 * (size_t)s.n);
+        s.vis_col = alloc_counted<float>(s, 3 * (size_t)s.n);
+    }
+    if (s.frame_pending) B200_CHECK(cudaStreamWaitEvent(s.stream, s.ev_frame_done, 0));   // staging still being read
+    launch_frame(s, s.frame_pos, s.frame_col, max_speed);
+    s.frame_has_prev = true;
+    float* dpos = to_device ? out_pos : s.vis_pos;
+    float* dcol = to_device ? out_col : s.vis_col;
+    vis_count_kernel<<<blocks, 256, 0, s.stream>>>(s.frame_pos, s.n, cam, s.vis_counts);
+    vis_scan_kernel<<<1, 1024, 0, s.stream>>>(s.vis_counts, blocks);
+    vis_compact_kernel<<<blocks, 256, 0, s.stream>>>(s.frame_pos, s.frame_col, s.n, cam, s.vis_counts, dpos, dcol);
+    s.launches += 3;
+    B200_CHECK(cudaGetLastError());
+    B200_CHECK(cudaMemcpyAsync(s.vis_total_host, s.vis_counts + blocks, sizeof(unsigned), cudaMemcpyDeviceToHost, s.stream));
+    sync_and_check(s);
+    const int64_t count = (int64_t)*s.vis_total_host;
+    if (!to_device && count > 0) {
+        B200_CHECK(cudaMemcpyAsync(out_pos, s.vis_pos, 3 * (size_t)count * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        B200_CHECK(cudaMemcpyAsync(out_col, s.vis_col, 3 * (size_t)count * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        B200_CHECK(cudaStreamSynchronize(s.stream));
+    }
+    return count;
 }
 
 void nbody_frame_wait(NBodySim& s)

@@ -127,6 +127,10 @@ struct NBodySim {
     bool frame_has_prev = false;                                       // frame_pos / frame_col hold the previous frame
     double *up_pos = nullptr, *up_vel = nullptr;                       // (N,3) f64 staging of a prefetched state
     bool frame_pending = false, upload_pending = false;
+    // live-viewer path: frustum cull + ordered compaction of the frame (lazily allocated)
+    float *vis_pos = nullptr, *vis_col = nullptr;                      // (N,3) f32 compacted visible bodies
+    unsigned* vis_counts = nullptr;                                    // per-block visible counts -> exclusive offsets; [blocks] = total
+    unsigned* vis_total_host = nullptr;                                // pinned
 
     // sharded sort (multi-GPU): padded exchange buffers of world * slice sorted (key, local position) pairs
     uint64_t* ms_keys = nullptr;
@@ -208,6 +212,11 @@ void nbody_get_perm(NBodySim& s, uint32_t* out);
 void nbody_frame_begin(NBodySim& s, double max_speed, float* host_pos, float* host_col);
 void nbody_frame_begin_rows(NBodySim& s, double max_speed, float* host_pos, float* host_col, int row_begin, int row_end);
 void nbody_frame_wait(NBodySim& s);
+// live-viewer path (nbody/simulation.py:403-434 compute_visibility_points + the mask gathers of draw() :926-927):
+// colours, creation-order fp32 frame, frustum test, stable compaction; the visible bodies go to host buffers or
+// (to_device) straight into device memory such as a mapped OpenGL VBO.  Returns the visible count.  Blocking.
+struct Camera { double pos[3], forward[3], right[3], up[3], tan_h, tan_v, far_dist; };
+int64_t nbody_visible_frame(NBodySim& s, double max_speed, const Camera& cam, float* out_pos, float* out_col, bool to_device);
 void nbody_frame_delta_begin(NBodySim& s, double max_speed, short* host_dpos, short* host_dcol);
 // state prefetch: H2D on a third stream into staging; commit swaps it in on the compute stream
 void nbody_set_state_begin(NBodySim& s, const double* pos, const double* vel);

@@ -150,6 +150,38 @@ class B200BarnesHutSimulation:
     def compute_colors(self, max_speed: float):
         _lib.check(self._L.b200_nbody_compute_colors(self._handle(), float(max_speed)))
 
+    def visible_frame(self, cam_pos, cam_forward, cam_right, cam_up, fov_v: float, aspect: float, far_dist: float,
+                      max_speed: float = 15.0):
+        """The live viewer's per-frame data in one device call: what NBodySimulation._update_gpu's
+        copies + _compute_visibility + draw()'s mask gathers produce (nbody/simulation.py:809-817, :880-904,
+        :926-927) -- `positions[visible_mask].astype(float32)`, `colors[visible_mask]` -- with the frustum test
+        and the gather done on the GPU.  fov_v in radians.  Returns (visible_pos (k,3) f32, visible_colors (k,3) f32),
+        views of buffers owned by the object (valid until the next call)."""
+        import math
+        half_v = fov_v / 2
+        half_h = math.atan(math.tan(half_v) * aspect)                       # nbody/simulation.py:887-888
+        cam = np.concatenate([np.asarray(cam_pos, np.float64).ravel(), np.asarray(cam_forward, np.float64).ravel(),
+                              np.asarray(cam_right, np.float64).ravel(), np.asarray(cam_up, np.float64).ravel(),
+                              [math.tan(half_h), math.tan(half_v), float(far_dist)]])
+        if cam.shape != (15,):
+            raise ValueError("camera vectors must have 3 components each")
+        if getattr(self, "_vis_buf", None) is None:
+            self._vis_buf = (np.empty((self.n, 3), np.float32), np.empty((self.n, 3), np.float32))
+        vp, vc = self._vis_buf
+        fp, count = C.POINTER(C.c_float), C.c_int64(0)
+        _lib.check(self._L.b200_nbody_visible_frame(self._handle(), float(max_speed), cam.ctypes.data_as(C.POINTER(C.c_double)),
+                                                    vp.ctypes.data_as(fp), vc.ctypes.data_as(fp), C.byref(count)))
+        k = int(count.value)
+        return vp[:k], vc[:k]
+
+    def visible_frame_device(self, camera15, pos_device_ptr: int, col_device_ptr: int, max_speed: float = 15.0) -> int:
+        """Same, written to device memory (two (n,3) fp32 buffers, e.g. mapped OpenGL VBOs); returns the count."""
+        cam = np.ascontiguousarray(camera15, np.float64)
+        count = C.c_int64(0)
+        _lib.check(self._L.b200_nbody_visible_frame_device(self._handle(), float(max_speed), cam.ctypes.data_as(C.POINTER(C.c_double)),
+                                                           C.c_void_p(pos_device_ptr), C.c_void_p(col_device_ptr), C.byref(count)))
+        return int(count.value)
+
     @staticmethod
     def _out(out, shape, dtype):
         """Fresh array like the reference's getters, or a caller buffer (e.g. pinned host memory)."""

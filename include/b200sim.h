@@ -110,6 +110,20 @@ int b200_nbody_frame_wait(b200_nbody* h);
  * positions and colours in creation order; "previous frame" = the frame of the last frame_begin /
  * frame_delta_begin.  Half the device-to-host bytes of frame_begin.  Completed by frame_wait. */
 int b200_nbody_frame_delta_begin(b200_nbody* h, double max_speed, int16_t* pos_delta_out, int16_t* col_delta_out);
+/* Live-viewer frame (replaces, per displayed frame, the compute_colors + get_positions + get_colors of
+ * NBodySimulation._update_gpu (nbody/simulation.py:809-817), the CPU frustum test compute_visibility_points (:403-434,
+ * called from _compute_visibility :880-904) and the boolean-mask gathers of draw() (:926-927)): colours and the
+ * creation-order fp32 frame are produced on the device, every body is tested against the view frustum there (the
+ * reference's fp64 arithmetic on float32 positions, margin 1.2, near 0.1), and the visible bodies are compacted IN
+ * CREATION ORDER (what positions[mask] gives).  camera = 15 doubles: cam_pos[3], cam_forward[3], cam_right[3],
+ * cam_up[3], tan(half_fov_h), tan(half_fov_v), far distance (fog_end).  pos_out / col_out: host buffers with room
+ * for (n,3) fp32; *count = number of visible bodies written.  Blocking. */
+int b200_nbody_visible_frame(b200_nbody* h, double max_speed, const double* camera, float* pos_out, float* col_out, int64_t* count);
+/* Same, but the visible bodies are written to DEVICE memory ((n,3) fp32 each) -- e.g. the two vertex buffer objects
+ * of nbody/simulation.py:936-937 mapped with cudaGraphicsResourceGetMappedPointer -- so a displayed frame moves only
+ * the 8-byte count over PCIe. */
+int b200_nbody_visible_frame_device(b200_nbody* h, double max_speed, const double* camera, void* pos_device, void* col_device,
+                                    int64_t* count);
 /* Asynchronous set_state: begin starts the host-to-device copies on a third stream into staging;
  * commit waits for them, then makes them the current state on the handle's stream; after commit the
  * host arrays may be reused.  Started one step ahead, the copy overlaps the previous step's kernels. */

@@ -178,6 +178,19 @@ def colors(vel, max_speed: float):
     return out
 
 
+def visibility_mask(positions, cam_pos, cam_forward, cam_right, cam_up, tan_h: float, tan_v: float, far_dist: float):
+    """compute_visibility_points (nbody/simulation.py:403-434), operation by operation in fp64 (numpy does not
+    contract): positions are what the viewer holds, i.e. the backend's float32 positions widened to float64 (:816)."""
+    p = np.asarray(positions, np.float64)
+    cp, f, r, u = (np.asarray(a, np.float64) for a in (cam_pos, cam_forward, cam_right, cam_up))
+    dx, dy, dz = p[:, 0] - cp[0], p[:, 1] - cp[1], p[:, 2] - cp[2]
+    z = dx * f[0] + dy * f[1] + dz * f[2]
+    x = dx * r[0] + dy * r[1] + dz * r[2]
+    y = dx * u[0] + dy * u[1] + dz * u[2]
+    hw, hh = z * tan_h * 1.2, z * tan_v * 1.2
+    return ~((z < 0.1) | (z > far_dist)) & (np.abs(x) < hw) & (np.abs(y) < hh)
+
+
 def direct_sum(pos, mass, G: float, softening: float, targets=None):
     pos, mass = _f64(pos), _f64(mass)
     if targets is None:
