@@ -45,7 +45,7 @@ PHASE_BYTES = {"keygen": 24 + 8, "sort": 8 + 8 * (12 + 12), "gather": 4 + 60 + 6
 
 def _traffic(workload: str, phase: str):
     """Measured DRAM bytes per launch/step of a phase from the committed ncu captures (profiles/)."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         with open(path) as f:
             e = json.load(f)[workload][phase]
@@ -637,13 +637,14 @@ def run_gpu(args):
     peaks, peak_src = _peaks()
     fp32_peak = _lib.fp32_peak_tflops(local)
     achieved = FLOP_PER_INTERACTION * m["inter_step"] / (m["trav_ms"] * 1e-3) / 1e12 / world   # per GPU
-    kernel = "traverse64_kernel" if m["stats"].get("trav_kernel") == 64 else "traverse_kernel"
+    kernel = "traverse64c_kernel" if m["stats"].get("trav_kernel") == 64 else "traverse_kernel"
     roofline = {
         "kernel": kernel, "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
         "frac": achieved / fp32_peak if fp32_peak else None,
         "traffic": (_traffic(key, "traverse") if world == 1 and n == cfg["num_bodies"] else None),
-        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r01_traffic.json); "
-                        "the kernel is instruction-issue / FP32 bound, its records are served from L2",
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r02_traffic.json): 116 B/body "
+                        "of it is the fused integration epilogue (permutation, velocities, positions in; next fp64 state out); "
+                        "the kernel is instruction-issue / FP32 bound (DRAM 3 % busy), its records are served from L2",
         "peak_source": "measured in this run: FFMA-chain microbenchmark (b200_fp32_peak_tflops); "
                        "MEASURED_PEAKS.json has no FP32 entry; nominal 148 SM x 128 x 2 x 1.965 GHz = 74.4",
         "algorithmic_flop_per_launch": FLOP_PER_INTERACTION * m["inter_step"] / world,
@@ -660,7 +661,9 @@ def run_gpu(args):
     phases = {}
     for k, v in m["phase"].items():
         e = {"ms": v}
-        if k in PHASE_BYTES and v > 0:
+        if k == "integrate" and v < 0.02:
+            e["note"] = "fused into the traversal kernel's epilogue (traverse.cuh finish_body): its 116 B/body move inside the traverse phase"
+        elif k in PHASE_BYTES and v > 0:
             nb = phase_bodies.get(k, n) if world > 1 else n
             gbs = PHASE_BYTES[k] * nb / (v * 1e-3) / 1e9
             e.update(algorithmic_bytes_per_body=PHASE_BYTES[k], bodies_this_rank=nb, achieved_gbs=gbs, frac_of_hbm_peak=gbs / peaks["hbm_gbs"])
@@ -687,7 +690,9 @@ def run_gpu(args):
         "data": "synthetic",
         "config": {"workload": key, "bodies": n, "theta": cfg["theta"], "G": cfg["G"], "softening": cfg["softening"],
                    "dt": cfg["dt"], "distribution": cfg["distribution"], "seed": 0,
-                   "parallelism": f"morton-range x{world}, replicated tree, allgather(acc)",
+                   "parallelism": (f"morton-range x{world}: sharded sort (NCCL all-gather of the sorted runs), replicated tree, each rank traverses + "
+                                   "integrates its range and stores the next state into every rank over NVLink peer mappings"
+                                   if world > 1 else "single GPU"),
                    "l2": "per-step working set >> 126 MB L2 (no flush needed)",
                    "state_dtype": "f64 positions/velocities, f32 forces"},
         "steps_per_sec": 1e3 / m["ms_per_step"],
@@ -707,13 +712,27 @@ def run_gpu(args):
         line["also"] = {"workload": "4k_collision_1m", "bodies": a["n"], "theta": a["cfg"]["theta"],
                         "value": a["value"], "unit": "body-updates/s", "ms_per_step": a["ms_per_step"],
                         "phases_ms": a["phase"], "interactions_per_body": a["inter_step"] / a["n"],
-                        "roofline": {"kernel": "traverse64_kernel" if a["stats"].get("trav_kernel") == 64 else "traverse_kernel",
+                        "roofline": {"kernel": "traverse64c_kernel" if a["stats"].get("trav_kernel") == 64 else "traverse_kernel",
                                      "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                                      "frac": ach / fp32_peak if fp32_peak else None},
                         "e2e": a.get("e2e"),
                         "cpu_baseline": cpu_baseline(a["cfg"], a["pos"], a["vel"], a["mass"])}
     if world == 1 and not args.no_also:
         line["also_boids"] = _measure_boids(args, torch, peaks)
+    if world == 1:
+        # the same law generated ON THE DEVICE straight into a handle (csrc/generate.cu), next to host_generate_s
+        import time as _t
+        from b200sim.nbody.gpu_backend import B200BarnesHutSimulation
+        t0 = _t.time()
+        g = B200BarnesHutSimulation.from_distribution(cfg["distribution"], n, cfg["spawn_radius"], cfg["G"], cfg["G"], cfg["softening"],
+                                                      cfg["damping"], cfg["theta"], seed=0, device=local)
+        g.sync()
+        line["device_generate_s"] = _t.time() - t0
+        line["device_generate_what"] = ("B200BarnesHutSimulation.from_distribution: allocation of the handle + Philox generation + radius "
+                                        "ranking (radix sort) + centre-of-mass shift on the device, no host arrays; the timed workload "
+                                        "itself is still the host-generated instance (host_generate_s) so the numbers stay comparable "
+                                        "across rounds")
+        g.close()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
