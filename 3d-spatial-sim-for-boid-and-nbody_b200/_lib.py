@@ -68,6 +68,8 @@ SIGNATURES = {
     "b200_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "b200_nbody_comm_init": (C.c_int, [_h, C.c_void_p, C.c_int, C.c_int]),
     "b200_nbody_world": (C.c_int, [_h, C.POINTER(C.c_int)]),
+    "b200_cost_weighted_split": (C.c_int, [C.POINTER(C.c_uint64), C.c_int, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_int64)]),
+    "b200_nbody_get_shard": (C.c_int, [_h, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "b200_nbody_destroy": (C.c_int, [_h]),
     "b200_nbody_step": (C.c_int, [_h, C.c_double]),
     "b200_nbody_step_n": (C.c_int, [_h, C.c_double, C.c_int]),

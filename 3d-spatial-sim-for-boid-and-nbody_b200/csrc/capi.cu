@@ -568,6 +568,24 @@ B200_API int b200_nbody_set_shard(b200_nbody* h, int64_t begin, int64_t end)
     return B200_OK;
 }
 
+B200_API int b200_cost_weighted_split(const uint64_t* chunk_cost, int nchunks, int64_t chunk, int64_t n, int world, int64_t* split_out)
+{
+    B200_ARG(chunk_cost && split_out && nchunks > 0 && chunk > 0 && n >= 0 && world >= 1, "bad argument");
+    B200_ARG((int64_t)nchunks * chunk >= n, "the chunks do not cover n");
+    B200_TRY({
+        const std::vector<int64_t> sp = b200::cost_weighted_split((const unsigned long long*)chunk_cost, nchunks, chunk, n, world);
+        for (int r = 0; r <= world; ++r) split_out[r] = sp[r];
+    })
+}
+
+B200_API int b200_nbody_get_shard(b200_nbody* h, int64_t* begin, int64_t* end)
+{
+    B200_ARG(h && begin && end, "null argument");
+    *begin = h->sim.shard_begin;
+    *end = h->sim.shard_end;
+    return B200_OK;
+}
+
 B200_API int b200_nbody_sharded_sort_setup(b200_nbody* h, int64_t slice, int world, void** keys_device_ptr, void** vals_device_ptr)
 {
     B200_ARG(h && keys_device_ptr && vals_device_ptr, "null argument");

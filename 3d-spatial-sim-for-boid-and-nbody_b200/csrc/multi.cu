@@ -20,6 +20,8 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -97,7 +99,18 @@ struct NBodyGroup {
     std::vector<void*> ipc_opened;                 // cudaIpcOpenMemHandle results to close
     int slice = 0;
     bool in_morton_order = false;                  // the state is in last step's Morton order: slices are key ranges
+    // cost-weighted Morton split: the traversal leaves a per-body cost (evaluated pair slots of its
+    // half tile) in acc.w; every `rebalance_every` steps the costs are summed per chunk of COST_CHUNK sorted
+    // positions, all-reduced (exact integer sums: every rank computes the same split) and the shard boundaries
+    // move to equal-cost chunk boundaries.  The sort slices stay equal-count.
+    std::vector<unsigned long long*> d_cost;       // per local replica: [nchunks]
+    unsigned long long* h_cost = nullptr;          // pinned
+    int nchunks = 0;
+    int rebalance_every = 8;
+    int64_t steps_since_reset = 0;
+    std::vector<int> split;                        // world + 1 boundaries (sorted positions) of the current shards
 };
+constexpr int COST_CHUNK = 4096;                   // a multiple of the 64-body tiles: shards are whole tiles
 
 static int slice_size(int n, int world)
 {
@@ -116,6 +129,76 @@ static void group_set_shards(NBodyGroup& g)
         s.shard_begin = (int)min((int64_t)r * g.slice, (int64_t)s.n);
         s.shard_end = (int)min((int64_t)(r + 1) * g.slice, (int64_t)s.n);
         nbody_ms_setup(s, g.slice, g.world);
+    }
+    g.steps_since_reset = 0;
+    if (!g.sims.empty()) {
+        const int n = g.sims[0]->n;
+        g.split.assign(g.world + 1, 0);
+        for (int r = 0; r <= g.world; ++r) g.split[r] = (int)min((int64_t)r * g.slice, (int64_t)n);
+        if (const char* e = getenv("B200_REBALANCE")) g.rebalance_every = atoi(e);
+        const int nchunks = div_up(n > 0 ? n : 1, COST_CHUNK);
+        if (g.world > 1 && g.rebalance_every > 0 && g.d_cost.empty()) {
+            g.nchunks = nchunks;
+            for (NBodySim* s : g.sims) {
+                B200_CHECK(cudaSetDevice(s->device));
+                g.d_cost.push_back(dev_alloc<unsigned long long>((size_t)nchunks));
+            }
+            B200_CHECK(cudaMallocHost(&g.h_cost, (size_t)nchunks * sizeof(unsigned long long)));
+        }
+    }
+}
+
+// cost of the rank's shard per chunk of sorted positions (zero outside the shard): one CTA per chunk
+__global__ void __launch_bounds__(256) shard_cost_kernel(const float4* __restrict__ acc, int begin, int end, unsigned long long* __restrict__ cost)
+{
+    const int lo = max(begin, (int)blockIdx.x * COST_CHUNK), hi = min(end, ((int)blockIdx.x + 1) * COST_CHUNK);
+    unsigned long long c = 0;
+    for (int k = lo + (int)threadIdx.x; k < hi; k += 256) c += (unsigned long long)(unsigned)__float_as_int(acc[k].w);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    __shared__ unsigned long long sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        cost[blockIdx.x] = t;
+    }
+}
+
+// equal-cost shard boundaries at chunk granularity from the all-reduced chunk costs (identical on every rank);
+// pure host arithmetic, exported as b200_cost_weighted_split for the CPU tests
+std::vector<int64_t> cost_weighted_split(const unsigned long long* cost, int C, int64_t chunk, int64_t n, int W)
+{
+    std::vector<int64_t> split(W + 1, 0);
+    split[W] = n;
+    unsigned long long total = 0;
+    for (int c = 0; c < C; ++c) total += cost[c];
+    if (total == 0 || C < W) {   // nothing to weigh: equal chunk counts
+        for (int r = 1; r < W; ++r) split[r] = std::min<int64_t>((int64_t)((int64_t)C * r / W) * chunk, n);
+        return split;
+    }
+    unsigned long long run = 0;
+    int c = 0;
+    for (int r = 1; r < W; ++r) {
+        const unsigned long long target = (unsigned long long)((long double)total * r / W);
+        while (c < C && run + cost[c] / 2 < target) run += cost[c++];       // the chunk boundary nearest to the target
+        const int lo_chunk = (int)(split[r - 1] / chunk) + 1;                // every rank keeps at least one chunk
+        const int hi_chunk = C - (W - r);
+        const int b = c < lo_chunk ? lo_chunk : (c > hi_chunk ? hi_chunk : c);
+        while (c < b) run += cost[c++];
+        split[r] = std::min<int64_t>((int64_t)b * chunk, n);
+    }
+    return split;
+}
+
+static void apply_cost_split(NBodyGroup& g, const unsigned long long* cost)
+{
+    const std::vector<int64_t> split = cost_weighted_split(cost, g.nchunks, COST_CHUNK, g.sims[0]->n, g.world);
+    g.split.assign(split.begin(), split.end());
+    for (size_t i = 0; i < g.sims.size(); ++i) {
+        NBodySim& s = *g.sims[i];
+        s.shard_begin = (int)split[g.ranks[i]];
+        s.shard_end = (int)split[g.ranks[i] + 1];
     }
 }
 
@@ -236,6 +319,8 @@ void group_destroy(NBodyGroup* g)
         cudaSetDevice(s->device);
         cudaStreamSynchronize(s->stream);
     }
+    for (size_t i = 0; i < g->d_cost.size(); ++i) { cudaSetDevice(g->sims[i]->device); cudaFree(g->d_cost[i]); }
+    if (g->h_cost) cudaFreeHost(g->h_cost);
     for (void* p : g->ipc_opened) cudaIpcCloseMemHandle(p);
     for (ncclComm_t c : g->comms)
         if (c) nccl().CommDestroy(c);
@@ -244,8 +329,14 @@ void group_destroy(NBodyGroup* g)
 
 int group_world(const NBodyGroup* g) { return g ? g->world : 1; }
 
-// a new state was uploaded (creation order): the next step sorts everything on every rank
-void group_state_replaced(NBodyGroup* g) { if (g) g->in_morton_order = false; }
+// a new state was uploaded (creation order): the next step sorts everything on every rank, and the shards go back
+// to equal counts until the new order has been costed
+void group_state_replaced(NBodyGroup* g)
+{
+    if (!g) return;
+    g->in_morton_order = false;
+    group_set_shards(*g);
+}
 
 void group_step(NBodyGroup& g, double dt)
 {
@@ -266,17 +357,37 @@ void group_step(NBodyGroup& g, double dt)
     // 2. tree (replicated), 3. forces + integration + broadcast of the shard
     for (size_t i = 0; i < L; ++i) nbody_shard_build(*g.sims[i], sharded_sort);
     for (size_t i = 0; i < L; ++i) nbody_shard_traverse(*g.sims[i], dt, g.peers[i]);
-    // 4. the barrier that ends the step doubles as the reduction of the next bounds
+    // 4. the barrier that ends the step doubles as the reduction of the next bounds (and, on rebalancing steps, of
+    //    the shards' chunk costs)
+    ++g.steps_since_reset;
+    const bool rebalance = g.world > 1 && !g.d_cost.empty() && g.sims[0]->n > 0 &&
+                           (g.steps_since_reset == 1 || g.steps_since_reset % g.rebalance_every == 0);
+    if (rebalance)
+        for (size_t i = 0; i < L; ++i) {
+            NBodySim& s = *g.sims[i];
+            B200_CHECK(cudaSetDevice(s.device));
+            shard_cost_kernel<<<g.nchunks, 256, 0, s.stream>>>(s.acc, s.shard_begin, s.shard_end, g.d_cost[i]);
+            ++s.launches;
+            B200_CHECK(cudaGetLastError());
+        }
     if (g.world > 1) {
         B200_NCCL(nccl().GroupStart());
         for (size_t i = 0; i < L; ++i) {
             NBodySim& s = *g.sims[i];
             unsigned long long* m = nbody_shard_maxabs_next(s);
             B200_NCCL(nccl().AllReduce(m, m, 1, ncclUint64, ncclMax, g.comms[i], s.stream));
+            if (rebalance) B200_NCCL(nccl().AllReduce(g.d_cost[i], g.d_cost[i], (size_t)g.nchunks, ncclUint64, ncclSum, g.comms[i], s.stream));
         }
         B200_NCCL(nccl().GroupEnd());
     }
     for (size_t i = 0; i < L; ++i) nbody_shard_finish(*g.sims[i]);
+    if (rebalance) {   // one small read-back every `rebalance_every` steps: the shard bounds are launch arguments
+        NBodySim& s = *g.sims[0];
+        B200_CHECK(cudaSetDevice(s.device));
+        B200_CHECK(cudaMemcpyAsync(g.h_cost, g.d_cost[0], (size_t)g.nchunks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+        B200_CHECK(cudaStreamSynchronize(s.stream));
+        apply_cost_split(g, g.h_cost);
+    }
     g.in_morton_order = true;
 }
 

@@ -195,6 +195,7 @@ void group_destroy(NBodyGroup* g);
 int group_world(const NBodyGroup* g);
 void group_state_replaced(NBodyGroup* g);
 void group_step(NBodyGroup& g, double dt);
+std::vector<int64_t> cost_weighted_split(const unsigned long long* cost, int nchunks, int64_t chunk, int64_t n, int world);
 double fp32_peak_tflops(int device);
 void nbody_compute_colors(NBodySim& s, double max_speed);
 // after a synchronisation: throws StateError if a kernel raised a device error flag (sticky)

@@ -182,6 +182,12 @@ class B200BarnesHutSimulation:
                                                            C.c_void_p(pos_device_ptr), C.c_void_p(col_device_ptr), C.byref(count)))
         return int(count.value)
 
+    def get_shard(self):
+        """Sorted-position range this rank traverses + integrates (cost-weighted inside a multi-GPU group)."""
+        b, e = C.c_int64(0), C.c_int64(0)
+        _lib.check(self._L.b200_nbody_get_shard(self._handle(), C.byref(b), C.byref(e)))
+        return int(b.value), int(e.value)
+
     @staticmethod
     def _out(out, shape, dtype):
         """Fresh array like the reference's getters, or a caller buffer (e.g. pinned host memory)."""

@@ -180,6 +180,14 @@ int b200_nbody_create_multi(int64_t n, const double* pos, const double* vel, con
 int b200_nccl_unique_id(void* out128);
 int b200_nbody_comm_init(b200_nbody* h, const void* id128, int rank, int world);
 int b200_nbody_world(b200_nbody* h, int* world);
+/* Sorted-position range [begin, end) this rank currently traverses and integrates.  Inside a group the ranges are
+ * COST-WEIGHTED: the traversal leaves a per-body cost in the accelerations buffer, every 8 steps
+ * (B200_REBALANCE=k; 0 = keep equal counts) the costs are summed per 4096-body chunk, all-reduced, and the
+ * boundaries move to equal-cost chunk boundaries -- identical on every rank, results unchanged bit for bit. */
+int b200_nbody_get_shard(b200_nbody* h, int64_t* begin, int64_t* end);
+/* The split rule itself (pure host arithmetic, no device needed): world + 1 boundaries in sorted positions, multiples
+ * of `chunk`, from the per-chunk costs; every rank keeps at least one chunk; equal chunk counts when all costs are 0. */
+int b200_cost_weighted_split(const uint64_t* chunk_cost, int nchunks, int64_t chunk, int64_t n, int world, int64_t* split_out);
 
 /* ---- split sharded step (building blocks; the collectives are the caller's) -------------------
  * One process per GPU, every rank holds the full replicated state and builds the full tree;

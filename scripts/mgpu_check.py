@@ -23,11 +23,17 @@ mk = lambda: B200BarnesHutSimulation(pos, vel, mass, 0.1, 2.0, 1.0, 0.6, device=
 twin = mk()
 sh = ShardedSimulation(mk(), rank, world)
 ok = True
-for step in range(4):
+shards = set()
+for step in range(18):   # crosses the cost-weighted rebalancing of the shards (after steps 1, 8 and 16)
     sh.step(0.1); twin.step(0.1)
-    same = np.array_equal(sh.get_positions_f64(), twin.get_positions_f64()) and np.array_equal(sh.get_velocities(), twin.get_velocities())
-    ok &= same
-    print(f"[rank {rank}] step {step}: identical to the unsharded twin: {same}", flush=True)
+    shards.add(sh.get_shard())
+    if step < 3 or step in (8, 9, 17):
+        same = np.array_equal(sh.get_positions_f64(), twin.get_positions_f64()) and np.array_equal(sh.get_velocities(), twin.get_velocities())
+        ok &= same
+        print(f"[rank {rank}] step {step}: shard {sh.get_shard()} identical to the unsharded twin: {same}", flush=True)
+print(f"[rank {rank}] shard ranges seen: {sorted(shards)}", flush=True)
+if world > 1:
+    ok &= all(b % 4096 == 0 and (e % 4096 == 0 or e == n) for b, e in shards)   # cost-weighted boundaries (4096-body chunks), not the equal-count 64-body-tile split
 # sharded host traffic
 rng = np.random.default_rng(5)
 p2 = torch.from_numpy(pos + rng.normal(size=pos.shape)).pin_memory().numpy()

@@ -20,11 +20,16 @@ multi = B200BarnesHutSimulation(pos, vel, mass, 0.1, 2.0, 0.9995, 0.6, device_ma
 twin = B200BarnesHutSimulation(pos, vel, mass, 0.1, 2.0, 0.9995, 0.6, device=0)
 ok = multi.world() == bin(mask).count("1")
 print(f"world {multi.world()} (mask {mask:#x})", flush=True)
-for step in range(5):
+shards = set()
+for step in range(18):   # crosses the cost-weighted rebalancing of the shards (after steps 1, 8 and 16)
     multi.step(0.1); twin.step(0.1)
-    same = np.array_equal(multi.get_positions_f64(), twin.get_positions_f64()) and np.array_equal(multi.get_velocities(), twin.get_velocities())
-    ok &= same
-    print(f"step {step}: identical to the single-GPU twin: {same}", flush=True)
+    shards.add(multi.get_shard())
+    if step < 3 or step in (8, 9, 17):
+        same = np.array_equal(multi.get_positions_f64(), twin.get_positions_f64()) and np.array_equal(multi.get_velocities(), twin.get_velocities())
+        ok &= same
+        print(f"step {step}: shard of device 0 {multi.get_shard()}: identical to the single-GPU twin: {same}", flush=True)
+ok &= all(b % 4096 == 0 and (e % 4096 == 0 or e == n) for b, e in shards)   # cost-weighted boundaries (4096-body chunks), not the equal-count 64-body-tile split
+print(f"shard ranges of device 0 seen: {sorted(shards)}", flush=True)
 multi.set_state(pos * 1.01, vel); twin.set_state(pos * 1.01, vel)
 for step in range(3):
     multi.step(0.05); twin.step(0.05)

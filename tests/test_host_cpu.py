@@ -171,3 +171,36 @@ def test_dropin_injects_backend_into_reference_imports():
     import subprocess
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_cost_weighted_split_rule():
+    """shard boundaries from per-chunk traversal costs (pure host arithmetic of csrc/multi.cu, no GPU):
+    multiples of the chunk, monotone, every rank at least one chunk, each shard within one chunk's cost of the ideal
+    share, equal chunk counts when there is nothing to weigh, and the same answer on every call (ranks must agree)."""
+    import ctypes as C
+    from b200sim import _lib
+    L = _lib.load()
+
+    def split(cost, chunk, n, world):
+        cost = np.ascontiguousarray(cost, np.uint64)
+        out = np.zeros(world + 1, np.int64)
+        _lib.check(L.b200_cost_weighted_split(cost.ctypes.data_as(C.POINTER(C.c_uint64)), len(cost), chunk, n, world,
+                                              out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
+    rng = np.random.default_rng(0)
+    for world in (2, 3, 8):
+        for nchunks, n in ((49, 200_003), (12208, 50_000_000), (8, 32_768), (world, world * 4096)):
+            chunk = 4096
+            cost = (rng.gamma(0.7, 1000.0, nchunks) + 1).astype(np.uint64)      # strongly non-uniform density
+            sp = split(cost, chunk, n, world)
+            assert sp[0] == 0 and sp[-1] == n and np.all(np.diff(sp) > 0)
+            assert np.all(sp[1:-1] % chunk == 0)
+            assert np.array_equal(sp, split(cost, chunk, n, world))
+            if nchunks >= 4 * world:
+                csum = np.concatenate([[0], np.cumsum(cost.astype(np.float64))])
+                share = np.diff(csum[np.minimum(sp // chunk, nchunks)])
+                share[-1] = csum[-1] - csum[sp[-2] // chunk]
+                assert np.all(np.abs(share - csum[-1] / world) <= 1.01 * cost.max())
+            eq = split(np.zeros(nchunks, np.uint64), chunk, n, world)
+            assert eq[0] == 0 and eq[-1] == n and np.all(np.diff(eq) >= 0)
