@@ -581,6 +581,41 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
                 dist.all_reduce(el, op=dist.ReduceOp.MAX)
             return n * e2e_steps / float(el.item())
 
+        def pcie_probe():
+            # what the link gives this process: the 48 B/body upload alone, the 24 B/body read-back alone, and both at
+            # once (the steady-state e2e loop keeps both directions busy) -- the PCIe roofline of the e2e number
+            dpos = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+            dvel = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+            dfp = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+            dfc = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+            op_t, oc_t = torch.from_numpy(out_p[0]), torch.from_numpy(out_c[0])
+            s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+            def up():
+                with torch.cuda.stream(s_up):
+                    dpos.copy_(pin_pos, non_blocking=True); dvel.copy_(pin_vel, non_blocking=True)
+
+            def dn():
+                with torch.cuda.stream(s_dn):
+                    op_t.copy_(dfp, non_blocking=True); oc_t.copy_(dfc, non_blocking=True)
+
+            def t(fns):
+                for f in fns:
+                    f()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    for f in fns:
+                        f()
+                torch.cuda.synchronize()
+                return (time.perf_counter() - t0) / 2
+            t_up, t_dn, t_both = t([up]), t([dn]), t([up, dn])
+            return {"h2d_alone_gbs": 48 * n / t_up / 1e9, "d2h_alone_gbs": 24 * n / t_dn / 1e9,
+                    "both_directions_ms": 1e3 * t_both, "h2d_alone_ms": 1e3 * t_up, "d2h_alone_ms": 1e3 * t_dn,
+                    "bound_value": n / t_both, "bound_what": "bodies / time to move one step's 48 + 24 B/body over PCIe with both "
+                    "directions active and NOTHING else running: the e2e loop cannot beat this"}
+
+        pcie = pcie_probe() if world == 1 else None
         v_block = timed(run_blocking)
         v_pipe = timed(run_pipelined)
         steady_steps = max(e2e_steps, min(args.steps, 20))
@@ -596,6 +631,7 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
                       "pipeline": "steady state: timed with the pipeline full (one untimed prologue iteration); every timed "
                                   "iteration starts one 48 B/body upload, commits one, steps once and completes one 24 B/body "
                                   "frame; the closing synchronize covers the last frame and the last upload",
+                      "pcie": pcie,
                       "with_fill_and_drain_value": v_pipe, "with_fill_and_drain_steps": e2e_steps,
                       "what": "per step, through the ctypes C-ABI with pinned HOST buffers: set_state_begin/commit (H2D of "
                               "positions + velocities) + step + frame_begin/wait (colours, D2H of positions + colours); the "
