@@ -333,9 +333,126 @@ struct ChildrenArgs {
     unsigned char* __restrict__ ishead;
     int4* __restrict__ kids;
     unsigned* alloc; unsigned capacity; unsigned* error; unsigned* children_total;
+    // locally essential tree: null boxes = every cell is materialised
+    const int* __restrict__ boxes; const uint64_t* __restrict__ keys; const double* __restrict__ bounds; const float* __restrict__ ttab;
+    float eps2;
+    int shard_begin, shard_end;
 };
 
-__device__ __forceinline__ void count_children_block(int block, int n, const ChildrenArgs& a)
+// order-preserving float <-> int map (signed integer compare == float compare)
+__device__ __forceinline__ int let_f2ord(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float let_ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
+__global__ void __launch_bounds__(256) let_boxes_init_kernel(int* __restrict__ boxes)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < LET_BOXES * 6) boxes[t] = (t % 6) < 3 ? 0x7f7fffff : -0x7f7fffff;   // lo = +FLT_MAX, hi = -FLT_MAX (empty)
+}
+
+// Level-3 boxes: bounding box of the shard's bodies (the traversal's targets, sorted positions [begin, end)) per
+// 9-bit key prefix.  Neighbours in the sorted order share the prefix: a thread accumulates a running box while the
+// prefix stays the same, a CTA (4096 consecutive bodies) combines its threads in shared memory, and the global
+// atomics (six per CTA and prefix) stay far from the serialisation limit of the hot boxes of the dense core.
+constexpr int LET_L3 = 1 + 8 + 64;   // offset of the level-3 boxes
+constexpr int LET_CHUNK = 4096;
+__device__ __forceinline__ void let_flush(int* __restrict__ boxes, unsigned pre, const int mn[3], const int mx[3])
+{
+    for (int d = 0; d < 3; ++d) { atomicMin(&boxes[6 * (LET_L3 + pre) + d], mn[d]); atomicMax(&boxes[6 * (LET_L3 + pre) + 3 + d], mx[d]); }
+}
+__global__ void __launch_bounds__(256) let_boxes_kernel(const float4* __restrict__ posm, const uint64_t* __restrict__ keys, int begin, int end,
+                                                        int* __restrict__ boxes)
+{
+    __shared__ unsigned s_pre[256];
+    __shared__ int s_box[256][6];
+    const int base = begin + (int)blockIdx.x * LET_CHUNK;
+    unsigned cur = 0xffffffffu;
+    int mn[3] = {0x7f7fffff, 0x7f7fffff, 0x7f7fffff}, mx[3] = {-0x7f7fffff, -0x7f7fffff, -0x7f7fffff};
+    for (int j = 0; j < LET_CHUNK / 256; ++j) {
+        const int k = base + j * 256 + (int)threadIdx.x;
+        if (k >= end) break;
+        const float4 p = posm[k];
+        const unsigned pre = (unsigned)(keys[k] >> (63 - 3 * LET_LEVELS));
+        if (pre != cur) {
+            if (cur != 0xffffffffu) let_flush(boxes, cur, mn, mx);   // rare: the chunk crosses a prefix boundary
+            cur = pre;
+            for (int d = 0; d < 3; ++d) { mn[d] = 0x7f7fffff; mx[d] = -0x7f7fffff; }
+        }
+        const int o[3] = {let_f2ord(p.x), let_f2ord(p.y), let_f2ord(p.z)};
+        for (int d = 0; d < 3; ++d) { mn[d] = min(mn[d], o[d]); mx[d] = max(mx[d], o[d]); }
+    }
+    s_pre[threadIdx.x] = cur;
+    for (int d = 0; d < 3; ++d) { s_box[threadIdx.x][d] = mn[d]; s_box[threadIdx.x][3 + d] = mx[d]; }
+    __syncthreads();
+    // threads holding the same prefix as thread 0 are combined by the first six threads; the others flush themselves
+    const unsigned p0 = s_pre[0];
+    if (cur != 0xffffffffu && cur != p0) let_flush(boxes, cur, mn, mx);
+    if (threadIdx.x < 6 && p0 != 0xffffffffu) {
+        const int d = threadIdx.x;
+        int v = d < 3 ? 0x7f7fffff : -0x7f7fffff;
+        for (int t = 0; t < 256; ++t)
+            if (s_pre[t] == p0) v = d < 3 ? min(v, s_box[t][d]) : max(v, s_box[t][d]);
+        if (d < 3) atomicMin(&boxes[6 * (LET_L3 + p0) + d], v); else atomicMax(&boxes[6 * (LET_L3 + p0) + d], v);
+    }
+}
+
+// levels 2, 1, 0 = unions of the eight children (one CTA)
+__global__ void __launch_bounds__(512) let_boxes_up_kernel(int* __restrict__ boxes)
+{
+    const int off[4] = {0, 1, 9, 73};
+    for (int l = LET_LEVELS - 1; l >= 0; --l) {
+        const int cells = 1 << (3 * l);
+        for (int t = threadIdx.x; t < cells * 6; t += blockDim.x) {
+            const int c = t / 6, d = t % 6;
+            int v = d < 3 ? 0x7f7fffff : -0x7f7fffff;
+            for (int q = 0; q < 8; ++q) {
+                const int w = boxes[6 * (off[l + 1] + 8 * c + q) + d];
+                v = d < 3 ? min(v, w) : max(v, w);
+            }
+            boxes[6 * (off[l] + c) + d] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// May a body of the shard open the cell (level L, first sorted body's key)?  A body opens a cell iff
+// d^2(com, p) + eps^2 <= T.  The centre of mass lies in the cell's cube (the key prefix of its bodies) and p in one of
+// the level-3 boxes, so dist^2(cube, box) + eps^2 > T for every box means no body of the shard ever asks for the
+// cell's children.  The boxes form an octree (a parent box contains its children): the cell walks it from the top and
+// stops at the first level-3 box in range.  Conservative margins: the cube is widened by 1e-6 * bounds (float rounding
+// of positions and centres of mass is 6e-8 relative) and T by 1e-5.
+__device__ __forceinline__ bool let_needed(const float* __restrict__ sbox, int L, uint64_t key, double bounds, float T, float eps2)
+{
+    unsigned ix = 0, iy = 0, iz = 0;
+    for (int l = 0; l < L; ++l) {
+        const unsigned oct = (unsigned)(key >> (3 * (MORTON_LEVELS - 1 - l))) & 7u;
+        ix = 2u * ix + (oct & 1u); iy = 2u * iy + ((oct >> 1) & 1u); iz = 2u * iz + ((oct >> 2) & 1u);
+    }
+    const double size = ldexp(2.0 * bounds, -L), pad = 1e-6 * bounds;
+    const float clo[3] = {(float)(-bounds + ix * size - pad), (float)(-bounds + iy * size - pad), (float)(-bounds + iz * size - pad)};
+    const float chi[3] = {(float)(-bounds + (ix + 1) * size + pad), (float)(-bounds + (iy + 1) * size + pad), (float)(-bounds + (iz + 1) * size + pad)};
+    const float Tm = T * 1.00001f;
+    auto near = [&](int box) {   // (an empty box has lo = +FLT_MAX, hi = -FLT_MAX: never near)
+        const float* bx = sbox + 6 * box;
+        float d2 = eps2;
+        for (int d = 0; d < 3; ++d) {
+            const float q = fmaxf(fmaxf(bx[d] - chi[d], clo[d] - bx[3 + d]), 0.f);
+            d2 = fmaf(q, q, d2);
+        }
+        return d2 <= Tm;
+    };
+    if (!near(0)) return false;
+    for (int a = 0; a < 8; ++a) {
+        if (!near(1 + a)) continue;
+        for (int b = 0; b < 8; ++b) {
+            if (!near(9 + 8 * a + b)) continue;
+            for (int c = 0; c < 8; ++c)
+                if (near(73 + 64 * a + 8 * b + c)) return true;
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ void count_children_block(int block, int n, const ChildrenArgs& a, const float* __restrict__ sbox)
 {
     const int* __restrict__ childL = a.childL; const int* __restrict__ childR = a.childR; const int* __restrict__ parent = a.parent;
     const int2* __restrict__ range = a.range;
@@ -350,13 +467,19 @@ __device__ __forceinline__ void count_children_block(int block, int n, const Chi
     int Li = 0;
     int2 rg = make_int2(0, 0);
     bool head = false;
+    bool pruned = false;
     if (i < n - 1) {
         Li = lvl[i];
         const int par = parent[i];
         head = par < 0 || lvl[par] != Li;
         if (head) {
             rg = range[i];
-            if (Li >= MORTON_LEVELS) {
+            // (a cell holding bodies of the shard is kept without a test: keeping is always safe)
+            if (sbox && par >= 0 && (rg.y < a.shard_begin || rg.x >= a.shard_end))
+                pruned = !let_needed(sbox, Li, a.keys[rg.x], *a.bounds, a.ttab[Li], a.eps2);
+            if (pruned) {
+                cnt = 0;
+            } else if (Li >= MORTON_LEVELS) {
                 cnt = rg.y - rg.x + 1;
             } else {
                 int kid[KIDS];
@@ -417,12 +540,26 @@ __device__ __forceinline__ void count_children_block(int block, int n, const Chi
     // one 16-byte record per octree cell: everything write_records needs about a child cell
     if (!head) return;
     if (s_base == 0xffffffffu) cnt = 0;
-    meta[i] = make_int4(rg.x, rg.y, cnt ? (int)(s_base + wsum[warp] + inc - npair) : -1, (cnt << 5) | Li);
+    // a pruned cell keeps its own record in the parent (mass, centre, threshold) and says so in the child count
+    meta[i] = make_int4(rg.x, rg.y, cnt ? (int)(s_base + wsum[warp] + inc - npair) : -1,
+                        (int)(((pruned ? PRUNED_NCHILD : (unsigned)cnt) << 5) | (unsigned)Li));
 }
 
 __global__ void __launch_bounds__(256) count_children_kernel(int n, ChildrenArgs ca)
 {
-    count_children_block((int)blockIdx.x, n, ca);
+    count_children_block((int)blockIdx.x, n, ca, nullptr);
+}
+
+// sharded step with the locally essential tree test: persistent CTAs load the shard's boxes into shared memory once
+__global__ void __launch_bounds__(256) count_children_let_kernel(int n, int nblocks, ChildrenArgs ca)
+{
+    __shared__ float sbox[6 * LET_BOXES];
+    for (int t = threadIdx.x; t < 6 * LET_BOXES; t += 256) sbox[t] = let_ord2f(ca.boxes[t]);
+    __syncthreads();
+    for (int block = (int)blockIdx.x; block < nblocks; block += (int)gridDim.x) {
+        count_children_block(block, n, ca, sbox);
+        __syncthreads();   // the block's shared scratch is reused by the next iteration
+    }
 }
 
 // Pair records: children 2j and 2j+1 of a cell share one 64-byte record laid out for packed
@@ -512,7 +649,8 @@ __global__ void __launch_bounds__(256, 6) write_records_kernel(int n, TreeView t
     bool h = false;
     if (i < n - 1 && ishead[i]) {
         mi = __ldg(&tv.meta[i]);
-        h = (mi.w >> 5) != 0;
+        const unsigned nc = (unsigned)mi.w >> 5;
+        h = nc != 0u && nc != PRUNED_NCHILD;
     }
     unsigned hm = __ballot_sync(0xffffffffu, h);
     if (!hm) return;
@@ -706,6 +844,7 @@ void nbody_alloc(NBodySim& s, int n)
     s.d_maxabs = alloc_counted<unsigned long long>(s, 2);
     s.d_bounds = alloc_counted<double>(s, 1);
     s.d_ttab = alloc_counted<float>(s, 32);
+    s.d_boxes = alloc_counted<int>(s, 6 * LET_BOXES);
     s.d_root = alloc_counted<int>(s, 1);
     s.d_alloc = alloc_counted<unsigned>(s, 1);
     s.d_tile_counter = alloc_counted<unsigned>(s, 1);
@@ -726,6 +865,7 @@ void nbody_alloc(NBodySim& s, int n)
         // (tests shrink these to exercise the bucketed un-permute at small n)
         if (const char* v = getenv("B200_UNPERM_MIN_N")) s.unperm_min_n = atoi(v);
         if (const char* v = getenv("B200_UNPERM_SHIFT")) s.unperm_shift = max(1, min(30, atoi(v)));
+        if (const char* v = getenv("B200_LET")) s.let_enabled = atoi(v) != 0;
         if (const char* v = getenv("B200_REC_CAPACITY")) s.rec_capacity_override = atoll(v);   // tests: force a record pool overflow
         const char* ng = getenv("B200_NO_GRAPH");   // plain launches instead of the captured step (debugging, A/B timing)
         s.use_graph = !(ng && ng[0] == '1');
@@ -760,7 +900,7 @@ void nbody_free(NBodySim& s)
     cudaFree(s.posm); cudaFree(s.acc); cudaFree(s.childL); cudaFree(s.childR); cudaFree(s.parent);
     cudaFree(s.range); cudaFree(s.ploc); cudaFree(s.bex); cudaFree(s.meta); cudaFree(s.ishead);
     cudaFree(s.lvl); cudaFree(s.kids);
-    cudaFree(s.recs); cudaFree(s.colors); cudaFree(s.stage); cudaFree(s.d_maxabs); cudaFree(s.d_bounds); cudaFree(s.d_ttab);
+    cudaFree(s.recs); cudaFree(s.colors); cudaFree(s.stage); cudaFree(s.d_maxabs); cudaFree(s.d_bounds); cudaFree(s.d_ttab); cudaFree(s.d_boxes);
     cudaFree(s.d_children);
     cudaFree(s.d_root); cudaFree(s.d_alloc); cudaFree(s.d_tile_counter); cudaFree(s.d_interactions);
     cudaFree(s.d_error);
@@ -913,10 +1053,21 @@ __global__ void __launch_bounds__(256) merge_runs_kernel(const uint64_t* __restr
         const int qb = q * slice;
         const int ql = max(0, min(slice, n - qb));
         int lo = 0, hi = 0;
-        if (q != r) {
+        if (q != r && ql > 0) {
             const uint64_t kf = mine[j0], kl = mine[j1];
-            if (q < r) { lo = count_le(rkeys + qb, 0, ql, kf); hi = count_le(rkeys + qb, lo, ql, kl); }
-            else { lo = count_lt(rkeys + qb, 0, ql, kf); hi = count_lt(rkeys + qb, lo, ql, kl); }
+            const uint64_t* __restrict__ run = rkeys + qb;
+            // the runs were Morton ranges one step ago: most lie entirely below or above the tile, which two loads
+            // decide without the two 23-step binary searches (46 dependent L2 misses per run and tile otherwise)
+            const uint64_t qf = run[0], qlast = run[ql - 1];
+            if (q < r) {
+                if (qlast <= kf) lo = hi = ql;
+                else if (qf > kl) lo = hi = 0;
+                else { lo = count_le(run, 0, ql, kf); hi = count_le(run, lo, ql, kl); }
+            } else {
+                if (qlast < kf) lo = hi = ql;
+                else if (qf >= kl) lo = hi = 0;
+                else { lo = count_lt(run, 0, ql, kf); hi = count_lt(run, lo, ql, kl); }
+            }
         }
         s_lo[q] = lo;
         s_hi[q] = hi;
@@ -1028,12 +1179,23 @@ static void build_after_sort(NBodySim& s, bool for_step)
     if (n > 1) {
         init_build_counters_kernel<<<1, 1, 0, st>>>(s.d_alloc, s.d_children);   // pair 0 is the root's
         const int nb = div_up(n, PFX_BLOCK);
+        // sharded step: only the cells a body of this rank's shard may open get their children written
+        const bool let = for_step && s.let_enabled && s.world > 1 && s.shard_end - s.shard_begin < n && s.shard_end > s.shard_begin;
+        if (let) {
+            let_boxes_init_kernel<<<div_up(6 * LET_BOXES, 256), 256, 0, st>>>(s.d_boxes);
+            let_boxes_kernel<<<div_up(s.shard_end - s.shard_begin, LET_CHUNK), 256, 0, st>>>(s.posm, s.keys[s.sorted_slot], s.shard_begin, s.shard_end, s.d_boxes);
+            let_boxes_up_kernel<<<1, 512, 0, st>>>(s.d_boxes);
+            s.launches += 3;
+        }
         const ChildrenArgs ca{s.childL, s.childR, s.parent, s.range, s.lvl, s.meta, s.ishead, s.kids,
                               s.d_alloc, (unsigned)(s.rec_capacity_override > 0 ? min(s.rec_capacity, s.rec_capacity_override) : s.rec_capacity),
-                              s.d_error, s.d_children};
+                              s.d_error, s.d_children,
+                              let ? s.d_boxes : nullptr, s.keys[s.sorted_slot], s.d_bounds, s.d_ttab, (float)(s.softening * s.softening),
+                              s.shard_begin, s.shard_end};
         prefix_kernel<<<nb, 256, 0, st>>>(pos_sorted, mass_sorted, n, s.ploc, s.bex);
         prefix_blocks_kernel<<<1, 1024, 0, st>>>(s.bex, nb);
-        count_children_kernel<<<div_up(n - 1, 256), 256, 0, st>>>(n, ca);
+        if (let) count_children_let_kernel<<<min(div_up(n - 1, 256), 8 * s.sm_count), 256, 0, st>>>(n, div_up(n - 1, 256), ca);
+        else count_children_kernel<<<div_up(n - 1, 256), 256, 0, st>>>(n, ca);
         s.launches += 3;
         B200_CHECK(cudaGetLastError());
     }
@@ -1388,8 +1550,8 @@ static void throw_if_flagged(unsigned flags)
 {
     if (!flags) return;
     char b[256];
-    snprintf(b, sizeof(b), "device error flags %#x (1 = traversal stack overflow, 2 = octree record pool overflow): "
-                           "forces of the affected step(s) are incomplete", flags);
+    snprintf(b, sizeof(b), "device error flags %#x (1 = traversal stack overflow, 2 = octree record pool overflow, 4 = a body "
+                           "asked for a cell the locally essential tree had pruned): forces of the affected step(s) are incomplete", flags);
     throw StateError{std::string(b)};
 }
 

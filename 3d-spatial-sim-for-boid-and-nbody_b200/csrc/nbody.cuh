@@ -41,7 +41,12 @@ constexpr int TRAV_COUNTERS = 8;     // interactions, pair slots, lane-pairs, ba
 
 enum NBodyPhase { PH_KEYGEN = 0, PH_SORT, PH_GATHER, PH_BUILD, PH_EXTRACT, PH_TRAVERSE, PH_EXCHANGE, PH_INTEGRATE, PH_COUNT };
 
-enum NBodyError { ERR_STACK_OVERFLOW = 1, ERR_RECORD_OVERFLOW = 2 };
+enum NBodyError { ERR_STACK_OVERFLOW = 1, ERR_RECORD_OVERFLOW = 2, ERR_PRUNED_CELL_OPENED = 4 };
+// locally essential tree test: bounding boxes of the shard's bodies per key prefix of 0, 1, 2 and 3 octree levels
+// (1 + 8 + 64 + 512 boxes, a small octree of boxes walked per cell)
+constexpr int LET_LEVELS = 3;
+constexpr int LET_BOXES = 1 + 8 + 64 + 512;
+constexpr unsigned PRUNED_NCHILD = 0x3ffffffu; // "children not materialised on this rank" in a record's child count
 
 struct NBodySim {
     int n = 0;
@@ -113,6 +118,10 @@ struct NBodySim {
     // multi-GPU: this rank traverses sorted bodies [shard_begin, shard_end) (multiples of 32)
     int rank = 0, world = 1;
     int shard_begin = 0, shard_end = 0;
+    // locally essential tree (sharded step only): children records are written only for cells some body of the
+    // rank's shard may open (conservative box test); B200_LET=0 writes the whole tree on every rank
+    bool let_enabled = true;
+    int* d_boxes = nullptr;                   // [LET_BOXES][6] order-preserving ints: lo x,y,z, hi x,y,z of the shard's bodies per key prefix
 
     // asynchronous host traffic (frame egress / state prefetch), allocated on first use
     cudaStream_t up_stream = nullptr, down_stream = nullptr;

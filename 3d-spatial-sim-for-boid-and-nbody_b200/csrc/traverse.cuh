@@ -255,6 +255,11 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 4) traverse_kernel(const float4* _
                 n0 = __float_as_uint(fn.z); n1 = __float_as_uint(fn.w);
                 c0 = om.x != 0u && n0 != 0u;
                 c1 = om.y != 0u && n1 != 0u;
+                if ((c0 && n0 == PRUNED_NCHILD) || (c1 && n1 == PRUNED_NCHILD)) {   // see traverse64c_kernel
+                    atomicOr(error, (unsigned)ERR_PRUNED_CELL_OPENED);
+                    c0 = c0 && n0 != PRUNED_NCHILD;
+                    c1 = c1 && n1 != PRUNED_NCHILD;
+                }
             }
             const int np0 = (int)((n0 + 1u) >> 1), np1 = (int)((n1 + 1u) >> 1);
             const bool big = (c0 && np0 > TRAV_CHUNK_PAIRS) || (c1 && np1 > TRAV_CHUNK_PAIRS);
@@ -608,7 +613,12 @@ __global__ void __launch_bounds__(TRAV_BLOCK, 3) traverse64c_kernel(const float4
                 f0 = __float_as_uint(fn.x); f1 = __float_as_uint(fn.y);
                 c0n = __float_as_uint(fn.z); c1n = __float_as_uint(fn.w);
             }
-            const bool c0 = (om.x | om.z) != 0u && c0n != 0u, c1 = (om.y | om.w) != 0u && c1n != 0u;
+            bool c0 = (om.x | om.z) != 0u && c0n != 0u, c1 = (om.y | om.w) != 0u && c1n != 0u;
+            if ((c0 && c0n == PRUNED_NCHILD) || (c1 && c1n == PRUNED_NCHILD)) {   // cannot happen (locally essential tree test is conservative); never drop silently
+                atomicOr(error, (unsigned)ERR_PRUNED_CELL_OPENED);
+                c0 = c0 && c0n != PRUNED_NCHILD;
+                c1 = c1 && c1n != PRUNED_NCHILD;
+            }
             const int np0 = c0 ? (int)((c0n + 1u) >> 1) : 0, np1 = c1 ? (int)((c1n + 1u) >> 1) : 0;
             const bool bigc = np0 > TRAV_CELL_PAIRS || np1 > TRAV_CELL_PAIRS;
             if (!__any_sync(0xffffffffu, bigc)) {

@@ -40,7 +40,7 @@ typedef struct b200_nbody_stats {
     int64_t records;           /* octree records of the last tree: root + cells + leaves */
     int64_t interactions;      /* accepted body-node interactions since the last reset (device-counted) */
     double  bounds;            /* root half-size of the last tree: fma(max|coord|, 1.1, 10) */
-    uint32_t error_flags;      /* 0 = clean; 1 = traversal stack overflow; 2 = record pool overflow */
+    uint32_t error_flags;      /* 0 = clean; 1 = traversal stack overflow; 2 = record pool overflow; 4 = pruned cell opened */
     int32_t  sm_count;
     int64_t bytes_allocated;   /* device bytes owned by the handle */
     int64_t timed_steps;       /* steps accumulated in phase_ms */

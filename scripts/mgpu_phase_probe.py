@@ -57,6 +57,20 @@ if rank == 0:
     print(f"{key}: {n} bodies on {world} GPU(s): {1e3 * el.item() / steps:.3f} ms/step (wall, max over ranks, {steps} steps)", flush=True)
     for ln in lines:
         print(ln, flush=True)
+if world > 1 and "--nccl" in sys.argv:
+    # what NCCL itself needs for the sharded sort's exchange at this size: 8 B keys + 4 B positions per body
+    S = -(-n // world)
+    for dtype, name in ((torch.int64, "keys 8 B"), (torch.int32, "vals 4 B")):
+        buf = torch.zeros(S * world, dtype=dtype, device="cuda")
+        for _ in range(3):
+            dist.all_gather_into_tensor(buf, buf[rank * S:(rank + 1) * S])
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            dist.all_gather_into_tensor(buf, buf[rank * S:(rank + 1) * S])
+        torch.cuda.synchronize()
+        if rank == 0:
+            print(f"NCCL all-gather of the {name}/body slices ({S * buf.element_size() / 1e6:.0f} MB per rank): {(time.perf_counter() - t0) * 100:.3f} ms", flush=True)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
