@@ -1029,6 +1029,26 @@ __device__ __forceinline__ int count_lt(const uint64_t* __restrict__ run, int lo
     return lo;
 }
 
+// number of elements <= k (le) or < k (!le) of the sorted run, known to lie in [lo, hi]: the whole warp probes 32
+// positions per round (all lanes pass the same arguments and get the same result)
+__device__ __forceinline__ int warp_count(const uint64_t* __restrict__ run, int lo, int hi, uint64_t k, bool le)
+{
+    const int lane = (int)lane_id();
+    while (hi - lo > 32) {
+        const int step = (hi - lo + 32) / 33;
+        const int idx = lo + (lane + 1) * step - 1;
+        bool pred = false;
+        if (idx < hi) { const uint64_t v = run[idx]; pred = le ? v <= k : v < k; }
+        const int c = __popc(__ballot_sync(0xffffffffu, pred));   // pred is monotone along the lanes
+        const int nlo = lo + c * step;
+        if (c < 32) hi = min(hi, lo + (c + 1) * step - 1);
+        lo = nlo;
+    }
+    bool pred = false;
+    if (lo + lane < hi) { const uint64_t v = run[lo + lane]; pred = le ? v <= k : v < k; }
+    return lo + __popc(__ballot_sync(0xffffffffu, pred));
+}
+
 // A CTA merges MERGE_TILE consecutive elements of one run.  The counts in every other run are monotone
 // along the tile, so one thread per other run brackets them with two full binary searches at the tile's
 // first and last key; runs that were Morton ranges one step ago barely interleave, the bracket is
@@ -1048,41 +1068,42 @@ __global__ void __launch_bounds__(256) merge_runs_kernel(const uint64_t* __restr
     if (j0 >= len) return;
     const int j1 = min(j0 + MERGE_TILE, len) - 1;     // last element of the tile
     const uint64_t* __restrict__ mine = rkeys + begin;
-    if ((int)threadIdx.x < world) {
-        const int q = (int)threadIdx.x;
+    // one warp per other run: 32-ary searches (5 dependent rounds of loads instead of 23) for the counts at the tile's
+    // first and last key; runs entirely below or above the tile are decided by two loads
+    for (int q = (int)(threadIdx.x >> 5); q < world; q += 8) {
         const int qb = q * slice;
         const int ql = max(0, min(slice, n - qb));
         int lo = 0, hi = 0;
         if (q != r && ql > 0) {
             const uint64_t kf = mine[j0], kl = mine[j1];
             const uint64_t* __restrict__ run = rkeys + qb;
-            // the runs were Morton ranges one step ago: most lie entirely below or above the tile, which two loads
-            // decide without the two 23-step binary searches (46 dependent L2 misses per run and tile otherwise)
             const uint64_t qf = run[0], qlast = run[ql - 1];
-            if (q < r) {
-                if (qlast <= kf) lo = hi = ql;
-                else if (qf > kl) lo = hi = 0;
-                else { lo = count_le(run, 0, ql, kf); hi = count_le(run, lo, ql, kl); }
-            } else {
-                if (qlast < kf) lo = hi = ql;
-                else if (qf >= kl) lo = hi = 0;
-                else { lo = count_lt(run, 0, ql, kf); hi = count_lt(run, lo, ql, kl); }
-            }
+            const bool le = q < r;
+            if (le ? qlast <= kf : qlast < kf) lo = hi = ql;
+            else if (le ? qf > kl : qf >= kl) lo = hi = 0;
+            else { lo = warp_count(run, 0, ql, kf, le); hi = warp_count(run, lo, ql, kl, le); }
         }
-        s_lo[q] = lo;
-        s_hi[q] = hi;
+        if (lane_id() == 0) { s_lo[q] = lo; s_hi[q] = hi; }
     }
     __syncthreads();
+    // the constant part of every element's rank (runs whose count does not change over the tile) is summed once
+    int base_rank = 0;
+    unsigned long long open_runs = 0ull;   // runs with a non-empty bracket: per-element searches
+    for (int q = 0; q < world; ++q) {
+        if (s_lo[q] == s_hi[q]) base_rank += s_lo[q];
+        else open_runs |= 1ull << q;
+    }
+#pragma unroll 4
     for (int j = j0 + (int)threadIdx.x; j <= j1; j += 256) {
         const uint64_t k = mine[j];
-        int rank = j;
-        for (int q = 0; q < world; ++q) {
-            const int lo = s_lo[q], hi = s_hi[q];
-            if (lo == hi) rank += lo;
-            else rank += q < r ? count_le(rkeys + q * slice, lo, hi, k) : count_lt(rkeys + q * slice, lo, hi, k);
+        const uint32_t v = rvals[begin + j];
+        int rank = j + base_rank;
+        for (unsigned long long m = open_runs; m; m &= m - 1) {
+            const int q = __ffsll((long long)m) - 1;
+            rank += q < r ? count_le(rkeys + q * slice, s_lo[q], s_hi[q], k) : count_lt(rkeys + q * slice, s_lo[q], s_hi[q], k);
         }
         keys_out[rank] = k;
-        vals_out[rank] = (uint32_t)begin + rvals[begin + j];   // local sort position -> position in the current arrays
+        vals_out[rank] = (uint32_t)begin + v;   // local sort position -> position in the current arrays
     }
 }
 

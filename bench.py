@@ -36,10 +36,11 @@ sys.path.insert(0, ROOT)
 FLOP_PER_INTERACTION = 20          # GPU-Gems-3 convention
 CPU_SAMPLE_BODIES = 1_000_000      # bounded CPU sample (full oracle step on this many bodies)
 # algorithmic HBM bytes per body per phase (DESIGN.md "Kernels"), fp64 master state
-# gather = physical reorder (4 + 60 R, 60 + 16 W) fused with the radix-tree topology (8 R, 25 W);
+# gather = physical reorder of positions / masses / ids (4 + 36 R, 36 + 16 W; velocities are fetched through the
+# permutation by the traversal's integration epilogue, never reordered) fused with the radix-tree topology (8 R, 25 W);
 # build = prefix sums (32 R, 32 W) + children lists / allocation (21 R, ~24 W);
 # extract = pair records (kids 16 + meta 16 + prefix sums 31 + leaves 16 R, ~50 W)
-PHASE_BYTES = {"keygen": 24 + 8, "sort": 8 + 8 * (12 + 12), "gather": 4 + 60 + 60 + 16 + 8 + 25,
+PHASE_BYTES = {"keygen": 24 + 8, "sort": 8 + 8 * (12 + 12), "gather": 4 + 36 + 36 + 16 + 8 + 25,
                "build": 64 + 45, "extract": 79 + 50, "integrate": 16 + 48 + 48}
 
 
