@@ -416,7 +416,7 @@ class B200BarnesHutSimulation:
         d["phase_ms"] = {name: st.phase_ms[i] for i, name in enumerate(_lib.PHASE_NAMES)}
         if st.error_flags:
             raise _lib.B200Error(f"device error flags {st.error_flags:#x} (1 = traversal stack overflow, "
-                                 "2 = octree record pool overflow)")
+                                 "2 = octree record pool overflow, 4 = a pruned cell of the locally essential tree was asked for)")
         return d
 
     # ---- lifetime --------------------------------------------------------------------------
