@@ -414,6 +414,18 @@ __global__ void __launch_bounds__(512) let_boxes_up_kernel(int* __restrict__ box
     }
 }
 
+// every third bit of a 63-bit key, compacted into 21 bits (the inverse of spread3)
+__device__ __forceinline__ unsigned let_compact3(uint64_t x)
+{
+    x &= 0x1249249249249249ull;
+    x = (x ^ (x >> 2)) & 0x10c30c30c30c30c3ull;
+    x = (x ^ (x >> 4)) & 0x100f00f00f00f00full;
+    x = (x ^ (x >> 8)) & 0x001f0000ff0000ffull;
+    x = (x ^ (x >> 16)) & 0x001f00000000ffffull;
+    x = (x ^ (x >> 32)) & 0x00000000001fffffull;
+    return (unsigned)x;
+}
+
 // May a body of the shard open the cell (level L, first sorted body's key)?  A body opens a cell iff
 // d^2(com, p) + eps^2 <= T.  The centre of mass lies in the cell's cube (the key prefix of its bodies) and p in one of
 // the level-3 boxes, so dist^2(cube, box) + eps^2 > T for every box means no body of the shard ever asks for the
@@ -422,11 +434,9 @@ __global__ void __launch_bounds__(512) let_boxes_up_kernel(int* __restrict__ box
 // of positions and centres of mass is 6e-8 relative) and T by 1e-5.
 __device__ __forceinline__ bool let_needed(const float* __restrict__ sbox, int L, uint64_t key, double bounds, float T, float eps2)
 {
-    unsigned ix = 0, iy = 0, iz = 0;
-    for (int l = 0; l < L; ++l) {
-        const unsigned oct = (unsigned)(key >> (3 * (MORTON_LEVELS - 1 - l))) & 7u;
-        ix = 2u * ix + (oct & 1u); iy = 2u * iy + ((oct >> 1) & 1u); iz = 2u * iz + ((oct >> 2) & 1u);
-    }
+    // cell index per axis at level L = the top L of the 21 bits of every third key bit
+    const unsigned ix = let_compact3(key) >> (MORTON_LEVELS - L), iy = let_compact3(key >> 1) >> (MORTON_LEVELS - L),
+                   iz = let_compact3(key >> 2) >> (MORTON_LEVELS - L);
     const double size = ldexp(2.0 * bounds, -L), pad = 1e-6 * bounds;
     const float clo[3] = {(float)(-bounds + ix * size - pad), (float)(-bounds + iy * size - pad), (float)(-bounds + iz * size - pad)};
     const float chi[3] = {(float)(-bounds + (ix + 1) * size + pad), (float)(-bounds + (iy + 1) * size + pad), (float)(-bounds + (iz + 1) * size + pad)};
