@@ -125,3 +125,28 @@ def test_morton_key_layout():
     assert int(k[3]) == int("000" + "111" * 20, 2)
     assert int(k[4]) == int("111" + "000" * 20, 2)
     assert int(k.max()) < 2 ** 63
+
+
+def test_visibility_mask_restatement_matches_the_reference_frustum_test():
+    """oracle.visibility_mask (the checker of the live-viewer path) against the reference's own
+    compute_visibility_points (nbody/simulation.py:403-434) where the reference tree is present."""
+    import math
+    from oracle import refimport
+    if not refimport.available():
+        pytest.skip("no reference tree")
+    ref = refimport.load()
+    rng = np.random.default_rng(5)
+    n = 50_000
+    pos = (rng.normal(size=(n, 3)) * [300.0, 20.0, 300.0]).astype(np.float32).astype(np.float64)   # float32 positions widened (:816)
+    eye = np.array([40.0, 120.0, 380.0])
+    f = -eye / np.linalg.norm(eye)
+    r = np.cross(f, [0.0, 1.0, 0.0]); r /= np.linalg.norm(r)
+    u = np.cross(r, f)
+    fov_v, aspect, far = math.radians(75), 16 / 9, 600.0
+    tan_h, tan_v = math.tan(math.atan(math.tan(fov_v / 2) * aspect)), math.tan(fov_v / 2)
+    mask = np.zeros(n, np.bool_)
+    ref.simulation.compute_visibility_points(pos, eye, f, r, u, tan_h, tan_v, far, mask, n)
+    mine = orc.visibility_mask(pos, eye, f, r, u, tan_h, tan_v, far)
+    assert 0 < mask.sum() < n
+    # (numba fastmath may contract the dot products: a body within an ulp of a frustum plane may flip)
+    assert int((mask != mine).sum()) <= 2
