@@ -276,9 +276,9 @@ def run_reference(args):
     sp, sv, sm = _cpu_sample(pos, vel, mass)
     del pos, vel, mass
     path = CpuPath(cfg, sp, sv, sm)
-    for _ in range(max(1, min(args.warmup, 2)) if path.kind == "reference" else min(args.warmup, 1)):
-        path.step()                                    # Numba JIT + first touch
-    steps = max(1, min(args.steps, 10))                # bounded: a substep on the sample takes seconds
+    for _ in range(max(1, args.warmup)):
+        path.step()                                    # Numba JIT + first touch, then W untimed substeps
+    steps = max(1, args.steps)                         # exactly K timed substeps (~0.9 s each on the bounded sample)
     times = [path.step() for _ in range(steps)]
     total = sum(sum(t) for t in times)
     n = path.n
