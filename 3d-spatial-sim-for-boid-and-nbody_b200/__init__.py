@@ -7,6 +7,6 @@ Host code is Python over a C-ABI CUDA library (include/b200sim.h) through ctypes
 no CPU path in this package.
 """
 from . import _lib  # noqa: F401
-from ._lib import B200Error  # noqa: F401
+from ._lib import B200Error, pinned_empty  # noqa: F401
 
-__all__ = ["B200Error", "nbody", "boids", "config", "presets"]
+__all__ = ["B200Error", "pinned_empty", "nbody", "boids", "config", "presets"]

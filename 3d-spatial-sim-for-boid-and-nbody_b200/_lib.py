@@ -112,6 +112,8 @@ SIGNATURES = {
     "b200_nbody_step_end": (C.c_int, [_h, C.c_double]),
     "b200_nbody_acc_buffer": (C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "b200_fp32_peak_tflops": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "b200_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "b200_host_free": (C.c_int, [C.c_void_p]),
     "b200_boids_create": (C.c_int, [C.c_int64, _dp, _dp, _dp, C.POINTER(BoidsParams), C.c_int, C.POINTER(_h)]),
     "b200_boids_destroy": (C.c_int, [_h]),
     "b200_boids_step": (C.c_int, [_h, C.c_double]),
@@ -136,8 +138,8 @@ def load():
     """Load (building first if the sources are newer) and type every entry point."""
     global _lib
     if _lib is None:
-        path = _build.LIB_PATH
-        if _build.is_stale():
+        path = os.environ.get("B200SIM_LIB") or _build.LIB_PATH     # B200SIM_LIB: an A/B build of the library (development)
+        if path == _build.LIB_PATH and _build.is_stale():
             try:
                 _build.build()
             except Exception as e:  # no nvcc on this box and no prebuilt library
@@ -173,3 +175,33 @@ def fp32_peak_tflops(device: int = 0) -> float:
     v = C.c_double(0.0)
     check(load().b200_fp32_peak_tflops(device, C.byref(v)))
     return float(v.value)
+
+
+class _PinnedBlock:
+    """Owner of one b200_host_alloc block; numpy arrays made by pinned_empty keep it alive through .base."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = C.c_void_p()
+        check(load().b200_host_alloc(int(nbytes), C.byref(self.ptr)))
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        ptr, self.ptr = getattr(self, "ptr", None), None
+        if ptr and _lib is not None:
+            _lib.b200_host_free(ptr)
+
+
+def pinned_empty(shape, dtype):
+    """numpy.empty in page-locked host memory (b200_host_alloc): the buffers to hand to frame_begin /
+    frame_delta_begin / set_state_begin so that the copies really overlap the next step.  The memory is
+    released when the last array viewing it is garbage-collected."""
+    import numpy as np
+    dt = np.dtype(dtype)
+    shape = (int(shape),) if np.isscalar(shape) else tuple(int(x) for x in shape)
+    count = 1
+    for x in shape:
+        count *= x
+    block = _PinnedBlock(max(count * dt.itemsize, 1))
+    raw = (C.c_char * block.nbytes).from_address(block.ptr.value)
+    raw._b200_block = block            # the ctypes array is the numpy array's base object: ties the lifetimes
+    return np.frombuffer(raw, dtype=dt, count=count).reshape(shape)

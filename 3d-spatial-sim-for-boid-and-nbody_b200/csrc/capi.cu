@@ -635,6 +635,20 @@ B200_API int b200_fp32_peak_tflops(int device, double* tflops)
     B200_TRY(*tflops = b200::fp32_peak_tflops(device))
 }
 
+B200_API int b200_host_alloc(int64_t bytes, void** out)
+{
+    B200_ARG(out, "out pointer is null");
+    *out = nullptr;
+    B200_ARG(bytes >= 0, "negative size");
+    B200_TRY(B200_CHECK(cudaHostAlloc(out, bytes > 0 ? (size_t)bytes : 1, cudaHostAllocPortable)))
+}
+
+B200_API int b200_host_free(void* ptr)
+{
+    if (!ptr) return B200_OK;
+    B200_TRY(B200_CHECK(cudaFreeHost(ptr)))
+}
+
 // ============================================================================ boids
 B200_API int b200_boids_create(int64_t n, const double* pos, const double* vel, const double* col,
                                const b200_boids_params* params, int device, b200_boids** out)

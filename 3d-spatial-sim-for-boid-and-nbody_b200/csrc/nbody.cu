@@ -1257,7 +1257,7 @@ static void traverse_launch_t(NBodySim& s, int mode, int begin, int end, const S
     const int stop = min(end, s.n);
     if (mode == 64) {
         const int tiles64 = div_up(stop - begin, 64);
-        const int blocks = min(div_up(tiles64, TRAV_WARPS), s.sm_count * 3);
+        const int blocks = min(div_up(tiles64, TRAV_WARPS), s.sm_count * B200_TRAV64_CTAS);
         traverse64c_kernel<COUNT, INTEG><<<blocks, TRAV_BLOCK, TRAV64C_SMEM_BYTES, st>>>(s.recs, s.posm, s.acc, begin, stop, eps2, (float)s.G,
                                                                                         s.d_tile_counter, s.d_interactions, s.d_error, so);
     } else {

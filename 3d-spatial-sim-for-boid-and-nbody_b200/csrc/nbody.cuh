@@ -29,11 +29,24 @@ namespace b200 {
 struct __align__(16) D4 { double x, y, z, w; };
 
 constexpr int MORTON_LEVELS = 21;
-constexpr int TRAV_BLOCK = 256;
+// (build-time knobs of the traversal, for A/B builds: scripts/build_variants.sh; the defaults are the shipped kernel)
+#ifndef B200_TRAV_BLOCK
+#define B200_TRAV_BLOCK 256
+#endif
+#ifndef B200_TRAV_CAP
+#define B200_TRAV_CAP 512
+#endif
+#ifndef B200_TRAV64_CTAS
+#define B200_TRAV64_CTAS 3           // resident CTAs per SM of the 64-body walk (launch bounds and grid size)
+#endif
+#ifndef B200_TRAV64_PAD
+#define B200_TRAV64_PAD 0            // extra dynamic shared memory per CTA (occupancy experiments)
+#endif
+constexpr int TRAV_BLOCK = B200_TRAV_BLOCK;
 constexpr int TRAV_WARPS = TRAV_BLOCK / 32;
 constexpr int TRAV_BATCH = 32;       // pair slots evaluated per batch
 constexpr int TRAV_AREA = TRAV_BATCH + 2;   // entries between staging areas (bank offset of 32 B)
-constexpr int TRAV_CAP = 512;        // stack entries per warp (only cells that must be opened are pushed)
+constexpr int TRAV_CAP = B200_TRAV_CAP;        // stack entries per warp (only cells that must be opened are pushed)
 constexpr int TRAV_DFS_MARK = 256;   // 32-body walk: above this many entries a batch pops only the top one
 constexpr int TRAV_RESERVE = 160;    // stack room kept free by the batch size limit (>= the depth-first bound 7 * 21)
 constexpr int TRAV_CELL_PAIRS = 4;    // pairs of an ordinary cell (<= 8 children); more = a finest-level bucket

@@ -385,7 +385,7 @@ struct __align__(16) WarpShared64C {
     float4 stage[5 * TRAV_AREA];         // class-sorted: XY ZM {T0,T1,mask lo,mask hi} {open lo 0, lo 1, hi 0, hi 1}; selection order: FN
     float4 box[4];                       // {Alo.xyz, -} {Ahi.xyz, -} {Blo.xyz, -} {Bhi.xyz, -}
 };
-constexpr size_t TRAV64C_SMEM_BYTES = sizeof(WarpShared64C) * TRAV_WARPS;
+constexpr size_t TRAV64C_SMEM_BYTES = sizeof(WarpShared64C) * TRAV_WARPS + B200_TRAV64_PAD;
 static_assert(2 * TRAV_CAP * sizeof(unsigned) >= 2 * 192 * sizeof(double), "the stack must hold a tile's staged state");
 constexpr float TRAV_SURE_MARGIN = 1.00001f;
 
@@ -426,7 +426,7 @@ __device__ __forceinline__ void eval_sure(const float4& XY, const float4& ZM, bo
 }
 
 template <bool COUNT, bool INTEG>
-__global__ void __launch_bounds__(TRAV_BLOCK, 3) traverse64c_kernel(const float4* __restrict__ recs, const float4* __restrict__ posm,
+__global__ void __launch_bounds__(TRAV_BLOCK, B200_TRAV64_CTAS) traverse64c_kernel(const float4* __restrict__ recs, const float4* __restrict__ posm,
                                                                     float4* __restrict__ acc, int begin, int end,
                                                                     float eps2, float G, unsigned* tile_counter,
                                                                     unsigned long long* counters, unsigned* error, const StepOut so)

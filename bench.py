@@ -491,7 +491,7 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
         hp, hv = pin_pos.numpy(), pin_vel.numpy()
         out_p = [torch.empty((n, 3), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
         out_c = [torch.empty((n, 3), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
-        e2e_steps = max(2, min(args.steps, 5))
+        e2e_steps = max(2, min(args.steps, 50))      # ~50 ms each
 
         def frame_blocking():
             sh.set_state(hp, hv)                   # H2D of the step's inputs
@@ -518,30 +518,31 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
             sh.frame_wait()
 
         def run_pipelined_steady(k):
-            # the same loop with the pipeline already full: one untimed prologue iteration, then k iterations
-            # each of which starts one upload (the inputs of the NEXT step), commits one, runs one step and
-            # completes one frame; the closing synchronize waits for the last frame AND the last upload, so
-            # exactly k uploads' and k frames' worth of copies complete inside the timed region.
+            # the same loop with the pipeline already full: one untimed prologue iteration, then k iterations each of
+            # which commits one upload, starts the next one (except the last: nothing dangles), runs one step and
+            # completes one frame.  The upload committed by the first timed iteration is started right before the
+            # clock (it runs inside the timed region), so exactly k uploads, k steps and k frames -- copies included --
+            # complete between t0 and the closing synchronize.  (scripts/e2e_timeline.py shows the steady cycle.)
             sh.set_state_begin(hp, hv)
             sh.set_state_commit()
-            sh.set_state_begin(hp, hv)
             sh.step(dt)
             sh.frame_begin(15.0, out_p[0], out_c[0])
+            sh.frame_wait()
+            torch.cuda.synchronize()               # prologue drained: no backlog of untimed work inside the timed region
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
+            sh.set_state_begin(hp, hv)
             for i in range(1, k + 1):
                 sh.set_state_commit()
-                sh.set_state_begin(hp, hv)
+                if i < k:
+                    sh.set_state_begin(hp, hv)
                 sh.step(dt)
                 sh.frame_wait()
                 sh.frame_begin(15.0, out_p[i & 1], out_c[i & 1])
             sh.frame_wait()
             torch.cuda.synchronize()
-            el = time.perf_counter() - t0
-            sh.set_state_commit()                  # (epilogue: the dangling upload)
-            torch.cuda.synchronize()
-            return el
+            return time.perf_counter() - t0
 
         out_dp = [torch.empty((n, 3), dtype=torch.int16).pin_memory().numpy() for _ in range(2)]
         out_dc = [torch.empty((n, 3), dtype=torch.int16).pin_memory().numpy() for _ in range(2)]
@@ -619,8 +620,8 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
         pcie = pcie_probe() if world == 1 else None
         v_block = timed(run_blocking)
         v_pipe = timed(run_pipelined)
-        steady_steps = max(e2e_steps, min(args.steps, 20))
-        run_pipelined_steady(1)
+        steady_steps = e2e_steps
+        run_pipelined_steady(2)
         el = torch.tensor([run_pipelined_steady(steady_steps)], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(el, op=dist.ReduceOp.MAX)
@@ -629,9 +630,9 @@ def _measure(key, bodies, args, rank, local, world, torch, dist, with_e2e=True, 
         v_rec = timed(run_recorder_loop)
         out["e2e"] = {"value": v_steady, "unit": "body-updates/s", "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 24 * n,
                       "steps": steady_steps,
-                      "pipeline": "steady state: timed with the pipeline full (one untimed prologue iteration); every timed "
-                                  "iteration starts one 48 B/body upload, commits one, steps once and completes one 24 B/body "
-                                  "frame; the closing synchronize covers the last frame and the last upload",
+                      "pipeline": "k iterations after one untimed (and drained) prologue iteration; exactly k 48 B/body uploads, k steps "
+                                  "and k 24 B/body frames start and complete inside the timed region (the closing synchronize "
+                                  "covers the last frame); uploads and read-backs overlap the neighbouring steps' kernels",
                       "pcie": pcie,
                       "with_fill_and_drain_value": v_pipe, "with_fill_and_drain_steps": e2e_steps,
                       "what": "per step, through the ctypes C-ABI with pinned HOST buffers: set_state_begin/commit (H2D of "

@@ -217,6 +217,13 @@ int b200_nbody_acc_buffer(b200_nbody* h, void** device_ptr, int64_t* capacity_en
 /* Measured FP32 FFMA throughput of the device (TFLOP/s): the traversal's roofline denominator. */
 int b200_fp32_peak_tflops(int device, double* tflops);
 
+/* Page-locked host memory for the asynchronous entry points (frame_begin, frame_delta_begin, set_state_begin):
+ * with pageable buffers -- what numpy.empty gives the reference's recorder (tools/record.py:828-829) -- the
+ * copies are staged by the driver and do not overlap the next step.  A caller without a CUDA binding of its own
+ * gets pinned buffers here; free with b200_host_free. */
+int b200_host_alloc(int64_t bytes, void** out);
+int b200_host_free(void* ptr);
+
 /* ---- boids ---------------------------------------------------------------------------------
  * The reference has no backend layer for boids; the seam is Flock.update(dt)
  * (boids/flock.py:627-678) mutating positions / velocities / colors (n,3) fp64.

@@ -1,24 +1,24 @@
-"""Timeline of the pipelined end-to-end frame loop (host timestamps around every call + device time of
-the step), to find where the loop loses time.  Development aid."""
+"""Host timestamps around every call of the pipelined frame loop (development aid, torch-free).
+    python scripts/e2e_timeline.py [frames: 0|1]"""
 import sys
 import time
 
 import numpy as np
-import torch
 
 sys.path.insert(0, ".")
 import b200sim  # noqa
-from b200sim import presets
+from b200sim import pinned_empty, presets
 from b200sim.nbody.gpu_backend import B200BarnesHutSimulation
 
-key = sys.argv[1] if len(sys.argv) > 1 else "extreme_50m_galaxy_t07"
-cfg, pos, vel, mass = presets.generate_preset(key, 0, None)
-n, dt = len(pos), cfg["dt"]
+frames = len(sys.argv) > 1 and sys.argv[1] == "1"
+cfg = presets.get_preset_config("extreme_50m_galaxy_t07")
+n, dt = cfg["num_bodies"], cfg["dt"]
+pos, vel, mass = presets.generate_distribution(cfg["distribution"], n, cfg["spawn_radius"], cfg["G"], seed=0)
+hp, hv = pinned_empty((n, 3), np.float64), pinned_empty((n, 3), np.float64)
+hp[:], hv[:] = pos, vel
+out_p = [pinned_empty((n, 3), np.float32) for _ in range(2)]
+out_c = [pinned_empty((n, 3), np.float32) for _ in range(2)]
 sim = B200BarnesHutSimulation(pos, vel, mass, cfg["G"], cfg["softening"], cfg["damping"], cfg["theta"])
-hp = torch.from_numpy(pos).pin_memory().numpy()
-hv = torch.from_numpy(vel).pin_memory().numpy()
-out_p = [torch.empty((n, 3), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
-out_c = [torch.empty((n, 3), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
 for _ in range(3):
     sim.step(dt)
 sim.sync()
@@ -26,20 +26,30 @@ rows = []
 T0 = time.perf_counter()
 
 
-def stamp(name, i):
-    rows.append((i, name, 1e3 * (time.perf_counter() - T0)))
+def call(name, i, fn):
+    t = 1e3 * (time.perf_counter() - T0)
+    fn()
+    rows.append((i, name, t, 1e3 * (time.perf_counter() - T0)))
 
 
-k = 6
 sim.set_state_begin(hp, hv)
-for i in range(k):
-    stamp("commit>", i); sim.set_state_commit(); stamp("commit<", i)
-    if i + 1 < k:
-        sim.set_state_begin(hp, hv); stamp("begin<", i)
-    sim.step(dt); stamp("step<", i)
-    sim.frame_wait(); stamp("frame_wait<", i)
-    sim.frame_begin(15.0, out_p[i & 1], out_c[i & 1]); stamp("frame_begin<", i)
-sim.frame_wait(); stamp("last_frame<", k)
-sim.sync(); stamp("sync<", k)
+sim.set_state_commit()
+sim.set_state_begin(hp, hv)
+sim.step(dt)
+if frames:
+    sim.frame_begin(15.0, out_p[0], out_c[0])
+T0 = time.perf_counter()
+for i in range(1, 6):
+    call("commit", i, sim.set_state_commit)
+    call("begin", i, lambda: sim.set_state_begin(hp, hv))
+    call("step", i, lambda: sim.step(dt))
+    if frames:
+        call("frame_wait", i, sim.frame_wait)
+        call("frame_begin", i, lambda: sim.frame_begin(15.0, out_p[i & 1], out_c[i & 1]))
+if frames:
+    call("frame_wait", 6, sim.frame_wait)
+call("sync", 6, sim.sync)
 for r in rows:
-    print("%d %-14s %9.2f" % r)
+    print("%d %-12s enter %8.2f  leave %8.2f  (%6.2f)" % (r[0], r[1], r[2], r[3], r[3] - r[2]))
+sim.set_state_commit()
+sim.close()

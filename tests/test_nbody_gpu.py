@@ -395,6 +395,36 @@ def test_async_frame_and_state_prefetch_match_blocking_calls():
         b.set_state_commit()                       # nothing pending
 
 
+def test_pinned_host_buffers_from_the_library():
+    """b200sim.pinned_empty (b200_host_alloc): numpy arrays in page-locked memory for the asynchronous entry
+    points, for callers without a CUDA binding of their own; same results as pageable buffers; the block is
+    released with the last view."""
+    import gc
+    import b200sim
+    from b200sim import presets
+    n = 5_000
+    pos, vel, mass = presets.generate("galaxy", n, 300.0, 0.1, 8)
+    sim = _sim(pos, vel, mass, 0.1, 2.0, theta=0.7)
+    fp, fc = b200sim.pinned_empty((n, 3), np.float32), b200sim.pinned_empty((n, 3), np.float32)
+    assert fp.shape == (n, 3) and fp.dtype == np.float32 and fp.flags.c_contiguous and fp.flags.writeable
+    hp, hv = b200sim.pinned_empty((n, 3), np.float64), b200sim.pinned_empty((n, 3), np.float64)
+    hp[:], hv[:] = pos[::-1], vel[::-1]
+    sim.set_state_begin(hp, hv)
+    sim.set_state_commit()
+    sim.step(0.05)
+    sim.frame_begin(15.0, fp, fc)
+    sim.frame_wait()
+    sim.compute_colors(15.0)
+    assert np.array_equal(fp, sim.get_positions()) and np.array_equal(fc, sim.get_colors())
+    view = fp[10:20]
+    del fp
+    gc.collect()
+    assert np.isfinite(view).all()                 # the view keeps the block alive
+    z = b200sim.pinned_empty(0, np.float64)
+    assert z.shape == (0,)
+    sim.close()
+
+
 def test_captured_step_is_bit_identical_to_plain_launches(monkeypatch):
     """step() replays CUDA graphs cached by (state buffer, parameters); the plain launches
     (B200_NO_GRAPH=1) must give the same bits through dt changes, a new state and a parameter change."""
