@@ -51,6 +51,22 @@ static_assert(sizeof(b200_boids_params) == sizeof(b200::BoidsParams), "boids par
         return B200_ERR_STATE;                           \
     }
 
+// constructors: free what was built, then the same status mapping as B200_TRY (nothing may unwind through extern "C")
+#define B200_CATCH_CREATE(cleanup)                       \
+    catch (const b200::CudaError& e) {                   \
+        b200::set_error(e.msg);                          \
+        cleanup;                                         \
+        return B200_ERR_CUDA;                            \
+    } catch (const b200::StateError& e) {                \
+        b200::set_error(e.msg);                          \
+        cleanup;                                         \
+        return B200_ERR_STATE;                           \
+    } catch (const std::exception& e) {                  \
+        b200::set_error(e.what());                       \
+        cleanup;                                         \
+        return B200_ERR_STATE;                           \
+    }
+
 #define B200_ARG(cond, text)                             \
     if (!(cond)) {                                       \
         b200::set_error(text);                           \
@@ -89,7 +105,7 @@ B200_API int b200_nbody_create(int64_t n, const double* pos, const double* vel, 
 {
     B200_ARG(out, "out handle is null");
     *out = nullptr;
-    B200_ARG(n >= 0 && n < (int64_t)1 << 30, "n out of range [0, 2^30)");
+    B200_ARG(n >= 0 && n < (int64_t)1 << 26, "n out of range [0, 2^26) (format limit of an n-body handle)");
     B200_ARG(n == 0 || (pos && vel && mass), "pos/vel/mass is null");
     B200_ARG(theta >= 0.0, "theta must be >= 0");
     b200_nbody* h = new b200_nbody();
@@ -101,12 +117,8 @@ B200_API int b200_nbody_create(int64_t n, const double* pos, const double* vel, 
         h->sim.theta = theta;
         b200::nbody_alloc(h->sim, (int)n);
         b200::nbody_upload(h->sim, pos, vel, mass);
-    } catch (const b200::CudaError& e) {
-        b200::set_error(e.msg);
-        b200::nbody_free(h->sim);
-        delete h;
-        return B200_ERR_CUDA;
     }
+    B200_CATCH_CREATE({ b200::nbody_free(h->sim); delete h; })
     *out = h;
     return B200_OK;
 }
@@ -143,7 +155,7 @@ B200_API int b200_nbody_create_generated(const char* distribution, int64_t n, do
     B200_ARG(out, "out handle is null");
     *out = nullptr;
     B200_ARG(distribution, "distribution name is null");
-    B200_ARG(n >= 0 && n < (int64_t)1 << 30, "n out of range [0, 2^30)");
+    B200_ARG(n >= 0 && n < (int64_t)1 << 26, "n out of range [0, 2^26) (format limit of an n-body handle)");
     B200_ARG(theta >= 0.0, "theta must be >= 0");
     b200_nbody* h = new b200_nbody();
     try {
@@ -154,12 +166,8 @@ B200_API int b200_nbody_create_generated(const char* distribution, int64_t n, do
         h->sim.theta = theta;
         b200::nbody_alloc(h->sim, (int)n);
         b200::nbody_generate(h->sim, b200::generator_id(distribution), R, G_dist, seed);
-    } catch (const b200::CudaError& e) {
-        b200::set_error(e.msg);
-        b200::nbody_free(h->sim);
-        delete h;
-        return B200_ERR_CUDA;
     }
+    B200_CATCH_CREATE({ b200::nbody_free(h->sim); delete h; })
     *out = h;
     return B200_OK;
 }
@@ -201,7 +209,7 @@ B200_API int b200_nbody_create_multi(int64_t n, const double* pos, const double*
 {
     B200_ARG(out, "out handle is null");
     *out = nullptr;
-    B200_ARG(n >= 0 && n < (int64_t)1 << 30, "n out of range [0, 2^30)");
+    B200_ARG(n >= 0 && n < (int64_t)1 << 26, "n out of range [0, 2^26) (format limit of an n-body handle)");
     B200_ARG(n == 0 || (pos && vel && mass), "pos/vel/mass is null");
     B200_ARG(theta >= 0.0, "theta must be >= 0");
     B200_ARG(device_mask != 0u, "empty device mask");
@@ -227,15 +235,8 @@ B200_API int b200_nbody_create_multi(int64_t n, const double* pos, const double*
             sims.push_back(s);
         }
         if (sims.size() > 1) h->group = b200::group_create_local(sims);
-    } catch (const b200::CudaError& e) {
-        b200::set_error(e.msg);
-        b200_nbody_destroy(h);
-        return B200_ERR_CUDA;
-    } catch (const b200::StateError& e) {
-        b200::set_error(e.msg);
-        b200_nbody_destroy(h);
-        return B200_ERR_STATE;
     }
+    B200_CATCH_CREATE(b200_nbody_destroy(h))
     *out = h;
     return B200_OK;
 }
@@ -665,12 +666,8 @@ B200_API int b200_boids_create(int64_t n, const double* pos, const double* vel, 
         memcpy(&h->sim.p, params, sizeof(b200::BoidsParams));
         b200::boids_alloc(h->sim, (int)n);
         b200::boids_upload(h->sim, pos, vel, col);
-    } catch (const b200::CudaError& e) {
-        b200::set_error(e.msg);
-        b200::boids_free(h->sim);
-        delete h;
-        return B200_ERR_CUDA;
     }
+    B200_CATCH_CREATE({ b200::boids_free(h->sim); delete h; })
     *out = h;
     return B200_OK;
 }

@@ -64,7 +64,9 @@ int b200_device_info(int device, char* name, int name_len);
 
 /* ---- n-body ------------------------------------------------------------------------------
  * create: replaces CUDASimulation.__init__ (nbody/gpu_backend.py:339-366) + theta of the
- * Metal Barnes-Hut twin.  Copies pos (n,3), vel (n,3), mass (n) [fp64] to the device. */
+ * Metal Barnes-Hut twin.  Copies pos (n,3), vel (n,3), mass (n) [fp64] to the device.
+ * 0 <= n < 2^26 bodies per handle (B200_ERR_ARG otherwise: the record format packs a cell's child count
+ * into 26 bits); the reference itself stops at an 8 M-node pool (nbody/simulation.py:35). */
 int b200_nbody_create(int64_t n, const double* pos, const double* vel, const double* mass,
                       double G, double softening, double damping, double theta,
                       int device, b200_nbody** out);

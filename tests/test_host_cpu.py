@@ -39,7 +39,15 @@ def test_argument_errors_raise_without_a_gpu():
     assert st == 2 and b"n out of range" in L.b200_last_error()
     with pytest.raises(_lib.B200Error):
         _lib.check(st)
+    # the format limit of a handle (2^26 bodies) is an argument error, not a CUDA failure later on
+    st = L.b200_nbody_create(1 << 26, None, None, None, 1.0, 1.0, 1.0, 0.5, 0, C.byref(h))
+    assert st == 2 and b"2^26" in L.b200_last_error() and not h.value
+    st = L.b200_nbody_create_generated(b"galaxy", 1 << 26, 1.0, 1.0, 0, 1.0, 1.0, 1.0, 0.5, 0, C.byref(h))
+    assert st == 2 and not h.value
     assert L.b200_nbody_step(None, 0.1) == 2
+    p = C.c_void_p()
+    assert L.b200_host_alloc(-1, C.byref(p)) == 2 and not p.value
+    assert L.b200_host_free(None) == 0
 
 
 def test_backend_module_surface_matches_reference():
