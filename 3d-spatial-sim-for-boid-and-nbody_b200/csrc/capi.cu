@@ -503,6 +503,7 @@ B200_API int b200_nbody_frame_wait(b200_nbody* h)
 B200_API int b200_nbody_set_state_begin(b200_nbody* h, const double* pos, const double* vel)
 {
     B200_ARG(h && ((pos && vel) || h->sim.n == 0), "null argument");
+    B200_ARG(h->others.empty(), "the asynchronous state prefetch is not available on a device-mask handle (use set_state)");
     B200_TRY(b200::nbody_set_state_begin(h->sim, pos, vel))
 }
 
@@ -510,6 +511,7 @@ B200_API int b200_nbody_set_state_begin_rows(b200_nbody* h, const double* pos, c
 {
     B200_ARG(h && ((pos && vel) || h->sim.n == 0), "null argument");
     B200_ARG(row_begin >= 0 && row_begin <= row_end && row_end <= h->sim.n, "rows out of range");
+    B200_ARG(h->others.empty(), "the asynchronous state prefetch is not available on a device-mask handle (use set_state)");
     B200_TRY(b200::nbody_set_state_begin_rows(h->sim, pos, vel, (int)row_begin, (int)row_end))
 }
 
