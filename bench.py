@@ -55,6 +55,15 @@ def _traffic(workload: str, phase: str):
         return None
 
 
+def _dispatch(workload: str):
+    """Dispatch-slot accounting of the traversal from the committed ncu per-pipe capture (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            return json.load(f)[workload]["traverse_dispatch"]
+    except Exception:
+        return None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -688,8 +697,12 @@ def run_gpu(args):
         "algorithmic_flop_per_launch": FLOP_PER_INTERACTION * m["inter_step"] / world,
         "interactions_per_body": m["inter_step"] / n, "launch_ms": m["trav_ms"],
         "interactions_counted": "on the same states as the timed traversals (a counting pass before every profiled step)",
-        "ceiling": "exact per-body MAC bounds this kernel at ~0.52 of FP32 peak on this workload (DESIGN.md section 4: "
-                   "0.62 useful interactions per evaluated lane-slot x 20/24 flop per FMA-pipe clock)",
+        "ceiling": "the kernel takes all of its SMSPs' dispatch slots (a packed fp32x2 instruction holds the port for 2 cycles: "
+                   "2 x packed + other instructions = 1.006 x the active cycles, see 'dispatch'), and more resident warps do not "
+                   "help (16 / 24 / 27 warps per SM: 28.2 / 26.0 / 26.05 ms): it is at the dispatch roofline of its instruction "
+                   "mix; with every non-arithmetic instruction free it would reach 0.59 of the FFMA peak (DESIGN.md section 4: "
+                   "0.63 useful interactions per evaluated lane-slot)",
+        "dispatch": (_dispatch(key) if world == 1 and n == cfg["num_bodies"] else None),
         "note": "per GPU; not tensor-core work (no dense contraction); HBM phases under 'phases'",
     }
     # HBM phases: bytes one rank moves / that rank's time.  With N > 1 the key generation and the radix sort run over the
